@@ -1,0 +1,981 @@
+// Host side of the B200 demodulation engine: configuration -> device tables and per-channel state, raw-sample
+// ingest, run scheduling (K1 then K2 per run), result queueing, and the C ABI declared in include/airband_b200.h.
+//
+// Config-time arithmetic restated here (host, double/float exactly as the reference does it):
+//   window                      reference src/rtl_airband.cpp:335-351
+//   sincos LUT                  reference src/util.cpp:103-111
+//   Squelch constructor/setters reference src/squelch.cpp:36-116
+//   Goertzel coefficients, bank reference src/ctcss.cpp:31-42,62-73,92-111
+//   NotchFilter coefficients    reference src/filters.cpp:30-47
+//   LowpassFilter design        reference src/filters.cpp:67-144
+//   initial channel state       reference src/config.cpp:265-281,313-331
+// There is no CPU execution path: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <complex>
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/airband_b200.h"
+#include "abg_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess) return fail(ABG_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+const float kStandardTones[51] = {67.0,  69.3,  71.9,  74.4,  77.0,  79.7,  82.5,  85.4,  88.5,  91.5,  94.8,  97.4,  100.0,
+                                  103.5, 107.2, 110.9, 114.8, 118.8, 123.0, 127.3, 131.8, 136.5, 141.3, 146.2, 150.0, 151.4,
+                                  156.7, 159.8, 162.2, 165.5, 167.9, 171.3, 173.8, 177.3, 179.9, 183.5, 186.2, 189.9, 192.8,
+                                  196.6, 199.5, 203.5, 206.5, 210.7, 218.1, 225.7, 229.1, 233.6, 241.8, 250.3, 254.1};  // ctcss.cpp:87-89
+
+// Goertzel coefficient of one detector, ctcss.cpp:31-42 (same operand types: int*float/float, +0.5 in double, float omega)
+float goertzel_coeff(float tone_freq, float sample_rate, int window_size) {
+    int k = (0.5 + window_size * tone_freq / sample_rate);
+    float omega = (2.0 * M_PI * k) / window_size;
+    float coeff = 2.0 * cos(omega);
+    return coeff;
+}
+// bank for one CTCSS object: wanted tone first, then standard tones not within 5 Hz, dropping coefficient collisions
+std::vector<float> tone_bank(float ctcss_freq, float sample_rate, int window_size) {
+    std::vector<float> coeffs;
+    auto try_add = [&](float f) {
+        float c = goertzel_coeff(f, sample_rate, window_size);
+        for (float e : coeffs)
+            if (e == c) return;
+        coeffs.push_back(c);
+    };
+    try_add(ctcss_freq);
+    for (float tone : kStandardTones) {
+        if (std::abs(ctcss_freq - tone) < 5) continue;
+        try_add(tone);
+    }
+    return coeffs;
+}
+
+// LowpassFilter::LowpassFilter, filters.cpp:67-96 (+ blt/expand/multin/eval :98-144)
+typedef std::complex<double> cd;
+cd lp_blt(cd pz) { return (2.0 + pz) / (2.0 - pz); }
+void lp_multin(cd w, int npz, cd coeffs[]) {
+    cd nw = -w;
+    for (int i = npz; i >= 1; i--) coeffs[i] = (nw * coeffs[i]) + coeffs[i - 1];
+    coeffs[0] = nw * coeffs[0];
+}
+bool lp_expand(cd pz[], int npz, cd coeffs[]) {
+    coeffs[0] = 1.0;
+    for (int i = 0; i < npz; i++) coeffs[i + 1] = 0.0;
+    for (int i = 0; i < npz; i++) lp_multin(pz[i], npz, coeffs);
+    for (int i = 0; i < npz + 1; i++)
+        if (fabs(coeffs[i].imag()) > 1e-10) return false;
+    return true;
+}
+cd lp_eval(cd coeffs[], int npz, cd z) {
+    cd sum(0.0);
+    for (int i = npz; i >= 0; i--) sum = (sum * z) + coeffs[i];
+    return sum;
+}
+bool lowpass_design(float freq, float sample_freq, float* gain, float* yc0, float* yc1) {
+    double raw_alpha = (double)freq / sample_freq;
+    double warped_alpha = tan(M_PI * raw_alpha) / M_PI;
+    cd zeros[2] = {-1.0, -1.0};
+    cd poles[2];
+    poles[0] = lp_blt(M_PI * 2 * warped_alpha * cd(-1.10160133059e+00, 6.36009824757e-01));
+    poles[1] = lp_blt(M_PI * 2 * warped_alpha * conj(cd(-1.10160133059e+00, 6.36009824757e-01)));
+    cd top[3], bot[3];
+    if (!lp_expand(zeros, 2, top) || !lp_expand(poles, 2, bot)) return false;
+    cd g = lp_eval(top, 2, 1.0) / lp_eval(bot, 2, 1.0);
+    *gain = hypot(g.imag(), g.real());
+    *yc0 = -(bot[0].real() / bot[2].real());
+    *yc1 = -(bot[1].real() / bot[2].real());
+    return true;
+}
+
+struct Plan {
+    int r1, r2, r3;
+};
+bool plan_for(int n, Plan* p) {  // must match Plan<LOGN> in k1_fft.cu
+    switch (n) {
+        case 256: *p = {16, 16, 0}; return true;
+        case 512: *p = {32, 16, 0}; return true;
+        case 1024: *p = {32, 32, 0}; return true;
+        case 2048: *p = {64, 32, 0}; return true;
+        case 4096: *p = {64, 64, 0}; return true;
+        case 8192: *p = {32, 16, 16}; return true;
+    }
+    return false;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+};
+
+struct Device {
+    int sfmt = 0, bpc = 0, sample_rate = 0, hop = 0, hop_bytes = 0;
+    float fullscale = 0;
+    int g0 = 0, C = 0, group = 0;
+    bool primed = false, has_afc = false;
+    // raw sample stream (ping-pong linear buffers)
+    unsigned char* raw[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t cap = 0, fill = 0, consumed = 0;
+    // resident replay stream
+    unsigned char* res = nullptr;
+    size_t res_bytes = 0;
+    bool res_primed = false;
+    float2* spec = nullptr;  // [nbmax][N] when has_afc
+    std::deque<std::pair<int, int>> ready;  // (slot, batch-in-run)
+};
+
+struct Group {
+    int sfmt, hop_bytes;
+    float fullscale;
+    std::vector<int> devs;
+    int frames_per_tile = 0, tile_bytes_cap = 0;
+    DevBuf<float> wsc;
+    K1Dev* d_k1 = nullptr;  // device array [devs.size()]
+    std::vector<K1Dev> h_k1;  // PAGEABLE staging on purpose: cudaMemcpyAsync snapshots pageable sources before returning
+};
+
+struct Slot {
+    float* wout = nullptr;    // pinned [G][nbmax*B]
+    float* iqout = nullptr;   // pinned [G][nbmax*B][2] or null
+    unsigned char* axc = nullptr;  // pinned [nbmax][Gp]
+    float* mix = nullptr;     // pinned [nbmax][n_mixers][2][B]
+    int32_t* mixflag = nullptr;  // pinned [nbmax][n_mixers]
+    int mix_pending = 0;
+    cudaEvent_t done = nullptr;
+    int pending = 0;          // unfetched device-batches referencing this slot
+};
+
+}  // namespace
+
+struct abg_engine {
+    int N = 0, W = 0, B = 0, fm_demod = 0, nbmax = 4, P = 0, G = 0, Gp = 0, fft_mode = 0;
+    int cuda_dev = 0;
+    bool any_iq_out = false;
+    std::vector<Device> dev;
+    std::vector<Group> groups;
+    std::vector<ChanParams> h_params;
+    // device memory
+    DevBuf<ChanParams> params;
+    DevBuf<ChanState> state;
+    DevBuf<int32_t> bins, base_bins;
+    DevBuf<float> win, wout, sqbuf, tone_coeff, tone_q1, tone_q2, tone_mag, lut;
+    DevBuf<float2> iqin, iqout, tw1, tw2;
+    DevBuf<unsigned char> axc;
+    K2Dev* d_k2 = nullptr;
+    std::vector<K2Dev> h_k2;  // pageable staging (see Group::h_k1)
+    std::vector<Slot> slots;
+    int next_slot = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // run start / after K1 / after K2 / run end
+    bool tev_valid = false;
+    std::vector<int32_t> h_bins;
+    // mixers (reference src/mixer.cpp)
+    int n_mixers = 0;
+    DevBuf<int32_t> mix_offsets;
+    DevBuf<MixInput> mix_inputs;
+    DevBuf<float> mix_sums;     // [nbmax][n_mixers][2][B]
+    DevBuf<int32_t> mix_flags;  // [nbmax][n_mixers]
+    std::deque<std::pair<int, int>> mix_ready;  // (slot, batch-in-run), same for every mixer
+    std::vector<int> mix_fetched;               // per mixer: entries of mix_ready already popped by that mixer
+
+    K2Launch k2_launch() const {
+        K2Launch L{};
+        L.G = G; L.Gp = Gp; L.P = P; L.wave_batch = B; L.fm_demod = fm_demod; L.iq_stride = nbmax * B;
+        L.params = params.p; L.state = state.p; L.devs = d_k2; L.bins = bins.p; L.base_bins = base_bins.p;
+        L.win = win.p; L.iqin = iqin.p; L.wout = wout.p; L.iqout = any_iq_out ? iqout.p : nullptr;
+        L.sqbuf = sqbuf.p; L.tone_coeff = tone_coeff.p; L.tone_q1 = tone_q1.p; L.tone_q2 = tone_q2.p; L.tone_mag = tone_mag.p;
+        L.axc = axc.p; L.sincos_lut = lut.p;
+        return L;
+    }
+};
+
+namespace {
+
+void engine_free(abg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cuda_dev);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& d : e->dev) {
+        for (int i = 0; i < 2; i++)
+            if (d.raw[i]) cudaFree(d.raw[i]);
+        if (d.res) cudaFree(d.res);
+        if (d.spec) cudaFree(d.spec);
+    }
+    for (auto& g : e->groups) {
+        g.wsc.free();
+        if (g.d_k1) cudaFree(g.d_k1);
+    }
+    e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win.free(); e->wout.free(); e->sqbuf.free();
+    e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin.free(); e->iqout.free();
+    e->tw1.free(); e->tw2.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
+    if (e->d_k2) cudaFree(e->d_k2);
+    for (auto& s : e->slots) {
+        if (s.wout) cudaFreeHost(s.wout);
+        if (s.iqout) cudaFreeHost(s.iqout);
+        if (s.axc) cudaFreeHost(s.axc);
+        if (s.mix) cudaFreeHost(s.mix);
+        if (s.mixflag) cudaFreeHost(s.mixflag);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto& ev : e->tev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int frames_available(const abg_engine* e, const Device& d, size_t fill, size_t consumed) {
+    // reference src/rtl_airband.cpp:394-400: a frame is taken only while available >= bps + fft_size*bytes_per_sample*2
+    const size_t avail = fill - consumed;
+    const size_t need = (size_t)d.hop_bytes + (size_t)e->N * d.bpc;
+    if (avail < need) return 0;
+    return (int)((avail - need) / d.hop_bytes) + 1;
+}
+
+int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
+    Plan plan;
+    if (!plan_for(cfg->fft_size, &plan)) return fail(ABG_EINVAL, "fft_size=%d not supported. Try a power of two between 256 and 8192.", cfg->fft_size);
+    if (cfg->wave_rate < 8 || cfg->wave_rate % 8) return fail(ABG_EINVAL, "wave_rate=%d must be a positive multiple of 8", cfg->wave_rate);
+    if (cfg->n_devices < 1 || !cfg->devices) return fail(ABG_EINVAL, "no devices configured");
+    e->N = cfg->fft_size;
+    e->W = cfg->wave_rate;
+    e->B = cfg->wave_rate / 8;  // WAVE_BATCH, rtl_airband.h:73
+    if (e->B < ABG_AGC_EXTRA) return fail(ABG_EINVAL, "wave_rate too small: WAVE_BATCH must be >= AGC_EXTRA");
+    e->fm_demod = cfg->fm_demod;
+    e->nbmax = (opt && opt->max_batches_per_run > 0) ? opt->max_batches_per_run : 4;
+    e->fft_mode = opt ? opt->fft_mode : 0;
+    const int in_cap_batches = (opt && opt->input_capacity_batches > 0) ? opt->input_capacity_batches : e->nbmax + 2;
+    e->P = ABG_AGC_EXTRA + e->nbmax * e->B;
+    const int N = e->N, B = e->B;
+
+    // ---- devices, channel index space ------------------------------------------------------------------------
+    e->dev.resize(cfg->n_devices);
+    int G = 0;
+    for (int i = 0; i < cfg->n_devices; i++) {
+        const abg_device_cfg& dc = cfg->devices[i];
+        Device& d = e->dev[i];
+        d.sfmt = dc.sfmt;
+        switch (dc.sfmt) {
+            case ABG_SFMT_U8: case ABG_SFMT_S8: d.bpc = 2; break;
+            case ABG_SFMT_S16: d.bpc = 4; break;
+            case ABG_SFMT_F32: d.bpc = 8; break;
+            default: return fail(ABG_EINVAL, "devices[%d]: unknown sample format %d", i, dc.sfmt);
+        }
+        if (dc.n_channels < 1 || !dc.channels) return fail(ABG_EINVAL, "devices[%d]: no channels configured", i);
+        if (dc.sample_rate <= cfg->wave_rate) return fail(ABG_EINVAL, "devices[%d]: sample_rate must be greater than %d", i, cfg->wave_rate);
+        if ((dc.sfmt == ABG_SFMT_S16 || dc.sfmt == ABG_SFMT_F32) && !(dc.fullscale > 0)) return fail(ABG_EINVAL, "devices[%d]: fullscale must be > 0", i);
+        d.sample_rate = dc.sample_rate;
+        d.fullscale = dc.fullscale;
+        d.hop = (int)round((double)dc.sample_rate / (double)cfg->wave_rate);  // rtl_airband.cpp:394
+        d.hop_bytes = d.hop * d.bpc;
+        d.g0 = G;
+        d.C = dc.n_channels;
+        G += dc.n_channels;
+    }
+    e->G = G;
+    e->Gp = (G + 31) & ~31;
+    const int Gp = e->Gp;
+
+    // ---- per-channel parameters and initial state ----------------------------------------------------------------
+    std::vector<ChanParams> hp(Gp);
+    std::vector<ChanState> hs(Gp);
+    std::vector<int32_t> hb(Gp, 0);
+    std::vector<float> h_coeff((size_t)2 * ABG_MAX_TONES * Gp, 0.0f);
+    memset(hp.data(), 0, sizeof(ChanParams) * Gp);
+    memset(hs.data(), 0, sizeof(ChanState) * Gp);
+    for (int i = 0; i < cfg->n_devices; i++) {
+        const abg_device_cfg& dc = cfg->devices[i];
+        Device& d = e->dev[i];
+        for (int c = 0; c < dc.n_channels; c++) {
+            const abg_channel_cfg& cc = dc.channels[c];
+            const int g = d.g0 + c;
+            if (cc.bin < 0 || cc.bin >= N) return fail(ABG_EINVAL, "devices[%d].channels[%d]: bin %d outside 0..%d", i, c, cc.bin, N - 1);
+            if (cc.modulation != ABG_MOD_AM && cc.modulation != ABG_MOD_NFM) return fail(ABG_EINVAL, "devices[%d].channels[%d]: unknown modulation", i, c);
+            ChanParams& p = hp[g];
+            ChanState& s = hs[g];
+            hb[g] = cc.bin;
+            p.dev = i;
+            p.modulation = cc.modulation;
+            p.needs_raw_iq = cc.needs_raw_iq ? 1 : 0;
+            p.has_iq_outputs = cc.has_iq_outputs ? 1 : 0;
+            if (p.has_iq_outputs) e->any_iq_out = true;
+            p.dm_dphi = cc.dm_dphi;
+            p.alpha = cc.alpha;
+            p.ampfactor = cc.ampfactor;
+            p.afc = cc.afc & 0xff;
+            if (p.afc) d.has_afc = true;
+            // ---- Squelch::Squelch(), squelch.cpp:36-82 ----
+            s.noise_floor = 5.0f;
+            s.manual = 0;
+            s.normal_ratio = pow(10.0, 9.54f / 20.0);
+            s.flappy_ratio = s.normal_ratio * 0.9f;
+            s.avg_cap = 1.5f * s.normal_ratio * s.noise_floor;
+            s.manual_level = -1.0;
+            s.pre_full = s.pre_capped = s.post_full = s.post_capped = 0.001f;
+            s.level_cache = 0.0f;
+            s.using_post = 0;
+            s.next_state = s.cur_state = SQ_CLOSED;
+            s.delay = 0;
+            s.sample_count_mod16 = 15u;  // sample_count_ = (size_t)-1: the first sample makes it 0 (squelch.cpp:58,204)
+            s.head = 0;
+            // ---- config.cpp:437-515: level first, then SNR ----
+            if (cc.squelch_level > 0) {  // set_squelch_level_threshold, squelch.cpp:84-96
+                s.manual = 1;
+                s.manual_level = cc.squelch_level;
+                s.avg_cap = 1.5f * s.manual_level;
+            }
+            if (cc.squelch_snr_db >= 0) {  // set_squelch_snr_threshold, squelch.cpp:98-108
+                s.manual = 0;
+                s.normal_ratio = pow(10.0, cc.squelch_snr_db / 20.0);
+                s.flappy_ratio = s.normal_ratio * 0.9f;
+                s.avg_cap = 1.5f * s.normal_ratio * s.noise_floor;
+            }
+            // ---- NotchFilter, filters.cpp:30-47 ----
+            if (cc.notch_hz > 0) {
+                float sample_freq = e->W, q = cc.notch_q;
+                float wo = 2 * M_PI * (cc.notch_hz / sample_freq);
+                float en = 1 / (1 + tan(wo / (q * 2)));
+                float pn = cos(wo);
+                p.notch_on = 1;
+                p.nd0 = en;
+                p.nd1 = 2 * en * pn;
+                p.nd2 = (2 * en - 1);
+            }
+            // ---- LowpassFilter, filters.cpp:67-96 ----
+            if (cc.lowpass_hz > 0) {
+                if (!lowpass_design(cc.lowpass_hz, (float)e->W, &p.lp_gain, &p.lp_yc0, &p.lp_yc1))
+                    return fail(ABG_EINVAL, "devices[%d].channels[%d]: lowpass design failed (poles not conjugate)", i, c);
+                p.lp_on = 1;
+            }
+            // ---- CTCSS, squelch.cpp:110-116 ----
+            if (cc.ctcss_hz > 0) {
+                const float sr = e->W;
+                p.ctcss_on = 1;
+                p.window[0] = sr * 0.05;
+                p.window[1] = sr * 0.4;
+                for (int w = 0; w < 2; w++) {
+                    std::vector<float> bank = tone_bank(cc.ctcss_hz, sr, p.window[w]);
+                    if ((int)bank.size() > ABG_MAX_TONES) return fail(ABG_EINVAL, "CTCSS bank too large");
+                    p.n_tones[w] = (int)bank.size();
+                    for (size_t t = 0; t < bank.size(); t++) h_coeff[((size_t)w * ABG_MAX_TONES + t) * Gp + g] = bank[t];
+                }
+            }
+            // ---- mk_freqlist / parse_channels initial values, config.cpp:265-281,313-331 ----
+            s.agcavgfast = 0.5f;
+            s.dm_phi = 0;
+            s.pr = s.pj = 0.0f;
+            s.prev_waveout = 0.5f;
+            s.axc_prev = ABG_NO_SIGNAL;
+        }
+    }
+    e->h_params = hp;
+    e->h_bins = hb;
+
+    // ---- tables -----------------------------------------------------------------------------------------------------
+    std::vector<float> window(N);
+    {  // rtl_airband.cpp:335-351
+        const double a0 = 0.27105140069342f, a1 = 0.43329793923448f, a2 = 0.21812299954311f, a3 = 0.06592544638803f;
+        const double a4 = 0.01081174209837f, a5 = 0.00077658482522f, a6 = 0.00001388721735f;
+        const size_t fft_size = N;
+        for (size_t i = 0; i < fft_size; i++) {
+            double x = a0 - (a1 * cos((2.0 * M_PI * i) / (fft_size - 1))) + (a2 * cos((4.0 * M_PI * i) / (fft_size - 1))) - (a3 * cos((6.0 * M_PI * i) / (fft_size - 1))) +
+                       (a4 * cos((8.0 * M_PI * i) / (fft_size - 1))) - (a5 * cos((10.0 * M_PI * i) / (fft_size - 1))) + (a6 * cos((12.0 * M_PI * i) / (fft_size - 1)));
+            window[i] = (float)x;
+        }
+    }
+    std::vector<float> h_lut(2 * 257);
+    for (uint32_t i = 0; i < 256; i++) sincosf(2.0F * M_PI * (float)i / 256.0f, &h_lut[i], &h_lut[257 + i]);  // util.cpp:105-110
+    h_lut[256] = h_lut[0];
+    h_lut[257 + 256] = h_lut[257];
+    const int M1 = N / plan.r1;
+    std::vector<float2> h_tw1((size_t)N);
+    for (int k1 = 0; k1 < plan.r1; k1++)
+        for (int n2 = 0; n2 < M1; n2++) {
+            double ang = -2.0 * M_PI * (double)(((long)k1 * n2) % N) / (double)N;
+            h_tw1[(size_t)k1 * M1 + n2] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    std::vector<float2> h_tw2;
+    if (plan.r3) {
+        const int M2 = plan.r3;
+        h_tw2.resize((size_t)plan.r2 * M2);
+        for (int k = 0; k < plan.r2; k++)
+            for (int n3 = 0; n3 < M2; n3++) {
+                double ang = -2.0 * M_PI * (double)(k * n3) / (double)M1;
+                h_tw2[(size_t)k * M2 + n3] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+    }
+
+    // ---- groups (one K1 launch per sample format / full-scale / hop) ------------------------------------------------------
+    for (int i = 0; i < (int)e->dev.size(); i++) {
+        Device& d = e->dev[i];
+        int gi = -1;
+        for (int k = 0; k < (int)e->groups.size(); k++)
+            if (e->groups[k].sfmt == d.sfmt && e->groups[k].hop_bytes == d.hop_bytes &&
+                (d.sfmt == ABG_SFMT_U8 || d.sfmt == ABG_SFMT_S8 || e->groups[k].fullscale == d.fullscale))
+                gi = k;
+        if (gi < 0) {
+            Group g;
+            g.sfmt = d.sfmt;
+            g.hop_bytes = d.hop_bytes;
+            g.fullscale = d.fullscale;
+            e->groups.push_back(g);
+            gi = (int)e->groups.size() - 1;
+        }
+        d.group = gi;
+        e->groups[gi].devs.push_back(i);
+    }
+
+    // ---- CUDA resources ----------------------------------------------------------------------------------------------------
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    for (auto& g : e->groups) {
+        g.frames_per_tile = abg_k1_tile_frames(N, g.sfmt, g.hop_bytes, &g.tile_bytes_cap);
+        if (g.frames_per_tile < 1) return fail(ABG_EINVAL, "fft_size=%d with this sample format does not fit shared memory", N);
+        // window * 1/full-scale: U8 levels are (i-127.5)/127.5, S8 i/128 (rtl_airband.cpp:319-324); S16/F32 scale = 1/fullscale (:403,421)
+        float scale = g.sfmt == ABG_SFMT_U8 ? 1.0f / 127.5f : g.sfmt == ABG_SFMT_S8 ? 1.0f / 128.0f : 1.0f / g.fullscale;
+        std::vector<float> wsc(N);
+        for (int i = 0; i < N; i++) wsc[i] = window[i] * scale;
+        CU(g.wsc.alloc(N));
+        CU(cudaMemcpy(g.wsc.p, wsc.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMalloc((void**)&g.d_k1, sizeof(K1Dev) * g.devs.size()));
+        g.h_k1.resize(g.devs.size());
+    }
+    for (auto& d : e->dev) {
+        // room for in_cap_batches batches + the AGC_EXTRA priming frames + one window, + slack for 16-byte TMA rounding
+        d.cap = ((size_t)(in_cap_batches * B + ABG_AGC_EXTRA) * d.hop_bytes + (size_t)N * d.bpc + (size_t)d.hop_bytes + 255) & ~(size_t)255;
+        for (int k = 0; k < 2; k++) {
+            cudaError_t er = cudaMalloc((void**)&d.raw[k], d.cap + 256);
+            if (er != cudaSuccess) return fail(ABG_ENOMEM, "Out of device memory for input buffers (%s)", cudaGetErrorString(er));
+            CU(cudaMemsetAsync(d.raw[k], 0, d.cap + 256, e->stream));
+        }
+        if (d.has_afc) CU(cudaMalloc((void**)&d.spec, sizeof(float2) * (size_t)e->nbmax * N));
+    }
+    const size_t PG = (size_t)e->P * Gp;
+    if (e->params.alloc(Gp) || e->state.alloc(Gp) || e->bins.alloc(Gp) || e->base_bins.alloc(Gp) || e->win.alloc(PG) || e->iqin.alloc(PG) ||
+        e->wout.alloc(PG) || e->sqbuf.alloc((size_t)ABG_SQ_BUF * Gp) || e->tone_coeff.alloc(h_coeff.size()) || e->tone_q1.alloc(h_coeff.size()) ||
+        e->tone_q2.alloc(h_coeff.size()) || e->tone_mag.alloc(h_coeff.size()) || e->lut.alloc(h_lut.size()) || e->tw1.alloc(h_tw1.size()) ||
+        e->tw2.alloc(std::max<size_t>(h_tw2.size(), 1)) || e->axc.alloc((size_t)e->nbmax * Gp) ||
+        (e->any_iq_out && e->iqout.alloc((size_t)Gp * e->nbmax * B)))
+        return fail(ABG_ENOMEM, "Out of device memory. Try fewer devices per GPU or a smaller max_batches_per_run.");
+    CU(cudaMemcpy(e->params.p, hp.data(), sizeof(ChanParams) * Gp, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->state.p, hs.data(), sizeof(ChanState) * Gp, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->bins.p, hb.data(), sizeof(int32_t) * Gp, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->base_bins.p, hb.data(), sizeof(int32_t) * Gp, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->tone_coeff.p, h_coeff.data(), sizeof(float) * h_coeff.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemset(e->tone_q1.p, 0, sizeof(float) * h_coeff.size()));
+    CU(cudaMemset(e->tone_q2.p, 0, sizeof(float) * h_coeff.size()));
+    CU(cudaMemset(e->tone_mag.p, 0, sizeof(float) * h_coeff.size()));
+    CU(cudaMemset(e->sqbuf.p, 0, sizeof(float) * ABG_SQ_BUF * Gp));  // calloc, squelch.cpp:70
+    CU(cudaMemcpy(e->lut.p, h_lut.data(), sizeof(float) * h_lut.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->tw1.p, h_tw1.data(), sizeof(float2) * h_tw1.size(), cudaMemcpyHostToDevice));
+    if (!h_tw2.empty()) CU(cudaMemcpy(e->tw2.p, h_tw2.data(), sizeof(float2) * h_tw2.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemset(e->iqin.p, 0, sizeof(float2) * PG));
+    if (e->any_iq_out) CU(cudaMemset(e->iqout.p, 0, sizeof(float2) * (size_t)Gp * e->nbmax * B));
+    {
+        // config.cpp:313-316: wavein[0..AGC_EXTRA) = 20, waveout[0..AGC_EXTRA) = 0.5.  (wavein's priming values are
+        // overwritten by the first AGC_EXTRA frames because waveend starts at 0, config.cpp:805; kept for fidelity.)
+        std::vector<float> hw(PG, 0.0f), ho(PG, 0.0f);
+        for (int k = 0; k < ABG_AGC_EXTRA; k++)
+            for (int g = 0; g < Gp; g++) hw[(size_t)k * Gp + g] = 20.0f;
+        for (int g = 0; g < Gp; g++)
+            for (int k = 0; k < ABG_AGC_EXTRA; k++) ho[(size_t)g * e->P + k] = 0.5f;
+        CU(cudaMemcpy(e->win.p, hw.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->wout.p, ho.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMalloc((void**)&e->d_k2, sizeof(K2Dev) * e->dev.size()));
+    e->h_k2.resize(e->dev.size());
+    e->slots.resize(3);
+    for (auto& s : e->slots) {
+        CU(cudaMallocHost((void**)&s.wout, sizeof(float) * (size_t)std::max(G, 1) * e->nbmax * B));
+        if (e->any_iq_out) CU(cudaMallocHost((void**)&s.iqout, sizeof(float2) * (size_t)std::max(G, 1) * e->nbmax * B));
+        CU(cudaMallocHost((void**)&s.axc, (size_t)e->nbmax * Gp));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    for (auto& ev : e->tev) CU(cudaEventCreate(&ev));
+    CU(cudaStreamSynchronize(e->stream));
+    return ABG_OK;
+}
+
+// enqueue K1 (+K2) for the per-device batch counts in nb[]; `resident` selects the replay buffers.
+int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool queue_outputs, int* n_enqueued) {
+    const int B = e->B, N = e->N;
+    int total = 0, nbrun = 0;
+    for (int v : nb) {
+        total += v;
+        nbrun = std::max(nbrun, v);
+    }
+    *n_enqueued = total;
+    if (total == 0) return ABG_OK;
+    int slot = -1;
+    if (queue_outputs) {
+        slot = e->next_slot;
+        if (e->slots[slot].pending > 0 || e->slots[slot].mix_pending > 0)
+            return fail(ABG_EOVERFLOW, "output overrun: %d finished batches not fetched yet", e->slots[slot].pending + e->slots[slot].mix_pending);
+        e->next_slot = (e->next_slot + 1) % (int)e->slots.size();
+    }
+    cudaStream_t st = e->stream;
+    CU(cudaEventRecord(e->tev[0], st));
+    // ---- K1 per group ----
+    for (auto& g : e->groups) {
+        int max_frames = 0;
+        for (size_t k = 0; k < g.devs.size(); k++) {
+            const int di = g.devs[k];
+            Device& d = e->dev[di];
+            K1Dev& a = g.h_k1[k];
+            const bool primed = resident ? d.res_primed : d.primed;
+            a.raw = resident ? d.res : d.raw[d.cur];
+            a.n_frames = nb[di] > 0 ? nb[di] * B + (primed ? 0 : ABG_AGC_EXTRA) : 0;
+            a.pos0 = primed ? ABG_AGC_EXTRA : 0;
+            a.start_byte = resident ? (primed ? (unsigned long long)ABG_AGC_EXTRA * d.hop_bytes : 0ull) : (unsigned long long)d.consumed;
+            a.g0 = d.g0;
+            a.n_channels = d.C;
+            a.hop_bytes = d.hop_bytes;
+            a.sfmt = d.sfmt;
+            a.spec = d.has_afc ? d.spec : nullptr;
+            a.spec_first_pos = ABG_AGC_EXTRA + B - 1;  // the frame that completes batch 0 of the run (waveend hits B+100)
+            a.wave_batch = B;
+            max_frames = std::max(max_frames, a.n_frames);
+        }
+        if (max_frames == 0) continue;
+        CU(cudaMemcpyAsync(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, st));
+        K1Launch L{};
+        L.fft_size = N; L.n_devices = (int)g.devs.size(); L.max_frames = max_frames; L.frames_per_tile = g.frames_per_tile;
+        L.tile_bytes_cap = g.tile_bytes_cap; L.devs = g.d_k1; L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p;
+        L.tw2 = e->tw2.p; L.win = e->win.p; L.iqin = e->iqin.p; L.Gp = e->Gp; L.sfmt = g.sfmt;
+        cudaError_t er = abg_launch_k1(L, st);
+        if (er != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er));
+        e->launches++;
+    }
+    CU(cudaEventRecord(e->tev[1], st));
+    // ---- K2 ----
+    for (size_t i = 0; i < e->dev.size(); i++) {
+        e->h_k2[i].n_batches = nb[i];
+        e->h_k2[i].fft_size = N;
+        e->h_k2[i].spec = e->dev[i].has_afc ? e->dev[i].spec : nullptr;
+    }
+    CU(cudaMemcpyAsync(e->d_k2, e->h_k2.data(), sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, st));
+    K2Launch L2 = e->k2_launch();
+    cudaError_t er = abg_launch_k2(L2, st);
+    if (er != cudaSuccess) return fail(ABG_ECUDA, "K2 launch failed: %s", cudaGetErrorString(er));
+    e->launches++;
+    CU(cudaEventRecord(e->tev[2], st));
+    // ---- mixers: sums over the just-finished batches, before the tail copy (output.cpp:533-535 -> mixer.cpp) ----
+    if (e->n_mixers > 0) {
+        MixLaunch M{};
+        M.n_mixers = e->n_mixers; M.n_batches = nbrun; M.wave_batch = B; M.P = e->P; M.Gp = e->Gp; M.offsets = e->mix_offsets.p;
+        M.inputs = e->mix_inputs.p; M.devs = e->d_k2; M.wout = e->wout.p; M.axc = e->axc.p; M.sums = e->mix_sums.p; M.flags = e->mix_flags.p;
+        er = abg_launch_mix(M, st);
+        if (er != cudaSuccess) return fail(ABG_ECUDA, "mixer launch failed: %s", cudaGetErrorString(er));
+        e->launches++;
+        if (queue_outputs) {
+            Slot& s = e->slots[slot];
+            CU(cudaMemcpyAsync(s.mix, e->mix_sums.p, sizeof(float) * (size_t)nbrun * e->n_mixers * 2 * B, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(s.mixflag, e->mix_flags.p, sizeof(int32_t) * (size_t)nbrun * e->n_mixers, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    // ---- results: D2H into the pinned slot, then the consumer's tail copy on the device ----
+    if (queue_outputs) {
+        Slot& s = e->slots[slot];
+        const size_t stride = (size_t)e->nbmax * B;
+        CU(cudaMemcpy2DAsync(s.wout, stride * sizeof(float), e->wout.p, (size_t)e->P * sizeof(float), (size_t)nbrun * B * sizeof(float), e->G,
+                             cudaMemcpyDeviceToHost, st));
+        if (e->any_iq_out)
+            CU(cudaMemcpy2DAsync(s.iqout, stride * sizeof(float2), e->iqout.p, stride * sizeof(float2), (size_t)nbrun * B * sizeof(float2), e->G,
+                                 cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(s.axc, e->axc.p, (size_t)nbrun * e->Gp, cudaMemcpyDeviceToHost, st));
+    }
+    er = abg_launch_k2_tail(L2, st);
+    if (er != cudaSuccess) return fail(ABG_ECUDA, "tail-copy launch failed: %s", cudaGetErrorString(er));
+    e->launches++;
+    if (queue_outputs) {
+        Slot& s = e->slots[slot];
+        CU(cudaEventRecord(s.done, st));
+        for (size_t i = 0; i < e->dev.size(); i++)
+            for (int b = 0; b < nb[i]; b++) {
+                e->dev[i].ready.emplace_back(slot, b);
+                s.pending++;
+            }
+        if (e->n_mixers > 0)
+            for (int b = 0; b < nbrun; b++) {
+                e->mix_ready.emplace_back(slot, b);
+                s.mix_pending += e->n_mixers;
+            }
+    }
+    CU(cudaEventRecord(e->tev[3], st));
+    e->tev_valid = true;
+    // ---- bookkeeping ----
+    for (size_t i = 0; i < e->dev.size(); i++) {
+        if (nb[i] <= 0) continue;
+        Device& d = e->dev[i];
+        if (resident) {
+            d.res_primed = true;
+        } else {
+            const int frames = nb[i] * B + (d.primed ? 0 : ABG_AGC_EXTRA);
+            d.consumed += (size_t)frames * d.hop_bytes;
+            d.primed = true;
+        }
+    }
+    return ABG_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================================
+// C ABI
+// =========================================================================================================================
+extern "C" {
+
+const char* abg_last_error(void) { return g_err.c_str(); }
+const char* abg_version(void) { return "airband-b200 0.1 (sm_100a)"; }
+
+int abg_create(const abg_config* cfg, const abg_options* opt, abg_engine** out) {
+    if (!cfg || !out) return fail(ABG_EINVAL, "abg_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t er = cudaGetDeviceCount(&ndev);
+    if (er != cudaSuccess || ndev < 1)
+        return fail(ABG_ENODEV, "Unable to find a CUDA device (%s). This engine has no CPU fallback.", er == cudaSuccess ? "device count is 0" : cudaGetErrorString(er));
+    abg_engine* e = new abg_engine();
+    if (opt && opt->cuda_device >= 0) {
+        e->cuda_dev = opt->cuda_device;
+        if (cudaSetDevice(e->cuda_dev) != cudaSuccess) {
+            delete e;
+            return fail(ABG_ENODEV, "cudaSetDevice(%d) failed", opt->cuda_device);
+        }
+    } else {
+        cudaGetDevice(&e->cuda_dev);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, e->cuda_dev) != cudaSuccess || prop.major < 10) {
+        int major = prop.major;
+        delete e;
+        return fail(ABG_ENODEV, "CUDA device has compute capability %d.x; this library contains sm_100a code only", major);
+    }
+    int rc = build(e, cfg, opt);
+    if (rc != ABG_OK) {
+        std::string keep = g_err;
+        engine_free(e);
+        g_err = keep;
+        return rc;
+    }
+    *out = e;
+    return ABG_OK;
+}
+
+void abg_destroy(abg_engine* e) { engine_free(e); }
+int abg_wave_batch(const abg_engine* e) { return e->B; }
+int abg_hop(const abg_engine* e, int dev) { return (dev < 0 || dev >= (int)e->dev.size()) ? ABG_ERANGE : e->dev[dev].hop; }
+
+int abg_push(abg_engine* e, int dev, const void* iq, size_t nbytes) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_push: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    if (nbytes == 0) return ABG_OK;
+    if (nbytes % d.bpc) return fail(ABG_EINVAL, "abg_push: %zu bytes is not a whole number of complex samples", nbytes);
+    cudaSetDevice(e->cuda_dev);
+    if (d.fill + nbytes > d.cap) {
+        // compact: move the unconsumed tail to the front of the other buffer (stream-ordered after any running K1).
+        // keep 16-byte alignment of the frame origin irrelevant: K1 aligns each tile itself.
+        const size_t keep_from = d.consumed & ~(size_t)15;  // keep the copy 16-byte aligned on both sides
+        const size_t rem = d.fill - keep_from;
+        if (rem + nbytes > d.cap) {
+            return fail(ABG_EOVERFLOW, "abg_push: device %d input buffer overflow (%zu buffered + %zu new > %zu)", dev, d.fill - d.consumed, nbytes, d.cap);
+        }
+        CU(cudaMemcpyAsync(d.raw[d.cur ^ 1], d.raw[d.cur] + keep_from, rem, cudaMemcpyDeviceToDevice, e->stream));
+        d.cur ^= 1;
+        d.fill = rem;
+        d.consumed -= keep_from;
+    }
+    CU(cudaMemcpyAsync(d.raw[d.cur] + d.fill, iq, nbytes, cudaMemcpyHostToDevice, e->stream));
+    d.fill += nbytes;
+    return ABG_OK;
+}
+
+int abg_batches_available(const abg_engine* e, int dev) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return ABG_ERANGE;
+    const Device& d = e->dev[dev];
+    const int frames = frames_available(e, d, d.fill, d.consumed) - (d.primed ? 0 : ABG_AGC_EXTRA);
+    return frames <= 0 ? 0 : frames / e->B;
+}
+
+int abg_run(abg_engine* e, int max_batches) {
+    cudaSetDevice(e->cuda_dev);
+    if (max_batches < 0 || max_batches > e->nbmax) max_batches = e->nbmax;
+    // AFC moves bins[] between batches (rtl_airband.cpp:629): with any AFC channel the run advances one batch at a
+    // time so that K1 of batch k+1 sees the bins K2 chose at the end of batch k.
+    for (auto& d : e->dev)
+        if (d.has_afc) max_batches = 1;
+    std::vector<int> nb(e->dev.size());
+    for (size_t i = 0; i < e->dev.size(); i++) nb[i] = std::min(max_batches, abg_batches_available(e, (int)i));
+    int n = 0;
+    int rc = enqueue_run(e, nb, false, true, &n);
+    return rc != ABG_OK ? rc : n;
+}
+
+int abg_sync(abg_engine* e) {
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream));
+    return ABG_OK;
+}
+
+int abg_batches_ready(abg_engine* e, int dev) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return ABG_ERANGE;
+    return (int)e->dev[dev].ready.size();
+}
+
+int abg_fetch_batch(abg_engine* e, int dev, float* waveout, float* iq_out, char* axcindicate) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_fetch_batch: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    if (d.ready.empty()) return 0;
+    const std::pair<int, int> r = d.ready.front();
+    Slot& s = e->slots[r.first];
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaEventSynchronize(s.done));
+    const int B = e->B;
+    const size_t stride = (size_t)e->nbmax * B;
+    for (int c = 0; c < d.C; c++) {
+        const size_t g = (size_t)d.g0 + c;
+        if (waveout) memcpy(waveout + (size_t)c * B, s.wout + g * stride + (size_t)r.second * B, sizeof(float) * B);
+        if (iq_out) {
+            if (s.iqout)
+                memcpy(iq_out + (size_t)c * 2 * B, s.iqout + 2 * (g * stride + (size_t)r.second * B), sizeof(float) * 2 * B);
+            else
+                memset(iq_out + (size_t)c * 2 * B, 0, sizeof(float) * 2 * B);
+        }
+        if (axcindicate) axcindicate[c] = (char)s.axc[(size_t)r.second * e->Gp + g];
+    }
+    d.ready.pop_front();
+    s.pending--;
+    return 1;
+}
+
+int abg_get_stats(abg_engine* e, int dev, int chan, abg_squelch_stats* out) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_get_stats: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    if (chan < 0 || chan >= d.C || !out) return fail(ABG_ERANGE, "abg_get_stats: channel %d out of range", chan);
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream));
+    ChanState s;
+    int32_t bin;
+    CU(cudaMemcpy(&s, e->state.p + d.g0 + chan, sizeof(s), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&bin, e->bins.p + d.g0 + chan, sizeof(bin), cudaMemcpyDeviceToHost));
+    out->noise_level = s.noise_floor;
+    out->signal_level = s.pre_full;
+    // Squelch::squelch_level(), squelch.cpp:164-177 (read-only evaluation)
+    if (s.manual)
+        out->squelch_level = s.manual_level;
+    else if (s.level_cache != 0.0f)
+        out->squelch_level = s.level_cache;
+    else
+        out->squelch_level = ((s.recent_open_count >= 3u && s.flappy_ratio < s.normal_ratio) ? s.flappy_ratio : s.normal_ratio) * s.noise_floor;
+    out->open_count = s.open_count;
+    out->flappy_count = s.flappy_count;
+    out->ctcss_count = s.ct_found[1];
+    out->no_ctcss_count = s.ct_not_found[1];
+    out->agcavgfast = s.agcavgfast;
+    out->dm_phi = s.dm_phi;
+    out->bin = bin;
+    out->active_counter = s.active_counter;
+    return ABG_OK;
+}
+
+int abg_set_bin(abg_engine* e, int dev, int chan, int bin) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_set_bin: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    if (chan < 0 || chan >= d.C) return fail(ABG_ERANGE, "abg_set_bin: channel %d out of range", chan);
+    if (bin < 0 || bin >= e->N) return fail(ABG_EINVAL, "abg_set_bin: bin %d outside 0..%d", bin, e->N - 1);
+    cudaSetDevice(e->cuda_dev);
+    int32_t v = bin;
+    CU(cudaMemcpyAsync(e->bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->base_bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return ABG_OK;
+}
+
+int abg_resident_load(abg_engine* e, int dev, const void* iq, size_t nbytes) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_resident_load: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    const size_t need = (size_t)(e->nbmax * e->B + ABG_AGC_EXTRA - 1) * d.hop_bytes + (size_t)e->N * d.bpc;
+    if (nbytes < need) return fail(ABG_EINVAL, "abg_resident_load: need at least %zu bytes for %d batches, got %zu", need, e->nbmax, nbytes);
+    cudaSetDevice(e->cuda_dev);
+    if (d.res) cudaFree(d.res);
+    d.res = nullptr;
+    if (cudaMalloc((void**)&d.res, need + 256) != cudaSuccess) return fail(ABG_ENOMEM, "Out of device memory for the resident stream");
+    d.res_bytes = need;
+    CU(cudaMemsetAsync(d.res + need, 0, 256, e->stream));
+    CU(cudaMemcpyAsync(d.res, iq, need, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return ABG_OK;
+}
+
+int abg_run_resident(abg_engine* e, int n_batches) {
+    cudaSetDevice(e->cuda_dev);
+    if (n_batches < 1 || n_batches > e->nbmax) return fail(ABG_EINVAL, "abg_run_resident: n_batches must be 1..%d", e->nbmax);
+    std::vector<int> nb(e->dev.size(), n_batches);
+    for (auto& d : e->dev)
+        if (!d.res) return fail(ABG_EINVAL, "abg_run_resident: abg_resident_load() was not called for every device");
+    int n = 0;
+    int rc = enqueue_run(e, nb, true, false, &n);
+    return rc != ABG_OK ? rc : n;
+}
+
+int abg_set_stream(abg_engine* e, void* cuda_stream) {
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)cuda_stream;
+    e->own_stream = false;
+    return ABG_OK;
+}
+
+uint64_t abg_launch_count(const abg_engine* e) { return e->launches; }
+
+int abg_last_run_times(abg_engine* e, float* ms4) {
+    if (!e->tev_valid) return fail(ABG_EINVAL, "abg_last_run_times: no run yet");
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaEventSynchronize(e->tev[3]));
+    CU(cudaEventElapsedTime(&ms4[0], e->tev[0], e->tev[1]));
+    CU(cudaEventElapsedTime(&ms4[1], e->tev[1], e->tev[2]));
+    CU(cudaEventElapsedTime(&ms4[2], e->tev[2], e->tev[3]));
+    CU(cudaEventElapsedTime(&ms4[3], e->tev[0], e->tev[3]));
+    return ABG_OK;
+}
+
+int abg_mixers_configure(abg_engine* e, int n_mixers, const int32_t* input_offsets, const abg_mixer_input* inputs) {
+    if (n_mixers < 0 || (n_mixers > 0 && (!input_offsets || !inputs))) return fail(ABG_EINVAL, "abg_mixers_configure: bad arguments");
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream));
+    if (!e->mix_ready.empty()) return fail(ABG_EINVAL, "abg_mixers_configure: unfetched mixer batches pending");
+    const int total = n_mixers ? input_offsets[n_mixers] : 0;
+    std::vector<MixInput> mi(total);
+    for (int i = 0; i < total; i++) {
+        const abg_mixer_input& in = inputs[i];
+        if (in.dev < 0 || in.dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "mixer input %d: device %d out of range", i, in.dev);
+        if (in.chan < 0 || in.chan >= e->dev[in.dev].C) return fail(ABG_ERANGE, "mixer input %d: channel %d out of range", i, in.chan);
+        mi[i].g = e->dev[in.dev].g0 + in.chan;
+        mi[i].dev = in.dev;
+        const float ampl = fminf(1.0f, 1.0f - in.balance), ampr = fminf(1.0f, 1.0f + in.balance);  // mixer.cpp:82-83
+        mi[i].mult_l = in.ampfactor * ampl;  // mixer.cpp:203,206
+        mi[i].mult_r = in.ampfactor * ampr;
+    }
+    e->mix_offsets.free(); e->mix_inputs.free(); e->mix_sums.free(); e->mix_flags.free();
+    for (auto& s : e->slots) {
+        if (s.mix) cudaFreeHost(s.mix);
+        if (s.mixflag) cudaFreeHost(s.mixflag);
+        s.mix = nullptr; s.mixflag = nullptr;
+    }
+    e->n_mixers = n_mixers;
+    e->mix_fetched.assign(n_mixers, 0);
+    if (n_mixers == 0) return ABG_OK;
+    const size_t nsum = (size_t)e->nbmax * n_mixers * 2 * e->B;
+    if (e->mix_offsets.alloc(n_mixers + 1) || e->mix_inputs.alloc(total) || e->mix_sums.alloc(nsum) || e->mix_flags.alloc((size_t)e->nbmax * n_mixers))
+        return fail(ABG_ENOMEM, "Out of device memory for mixers");
+    CU(cudaMemcpy(e->mix_offsets.p, input_offsets, sizeof(int32_t) * (n_mixers + 1), cudaMemcpyHostToDevice));
+    if (total) CU(cudaMemcpy(e->mix_inputs.p, mi.data(), sizeof(MixInput) * total, cudaMemcpyHostToDevice));
+    CU(cudaMemset(e->mix_sums.p, 0, sizeof(float) * nsum));
+    CU(cudaMemset(e->mix_flags.p, 0, sizeof(int32_t) * (size_t)e->nbmax * n_mixers));
+    for (auto& s : e->slots) {
+        CU(cudaMallocHost((void**)&s.mix, sizeof(float) * nsum));
+        CU(cudaMallocHost((void**)&s.mixflag, sizeof(int32_t) * (size_t)e->nbmax * n_mixers));
+    }
+    return ABG_OK;
+}
+
+int abg_fetch_mixer_batch(abg_engine* e, int mixer, float* left, float* right, int* has_signal) {
+    if (mixer < 0 || mixer >= e->n_mixers) return fail(ABG_ERANGE, "abg_fetch_mixer_batch: mixer %d out of range", mixer);
+    const int idx = e->mix_fetched[mixer];
+    if (idx >= (int)e->mix_ready.size()) return 0;
+    const std::pair<int, int> r = e->mix_ready[idx];
+    Slot& s = e->slots[r.first];
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaEventSynchronize(s.done));
+    const int B = e->B;
+    const float* base = s.mix + (((size_t)r.second * e->n_mixers + mixer) * 2) * B;
+    if (left) memcpy(left, base, sizeof(float) * B);
+    if (right) memcpy(right, base + B, sizeof(float) * B);
+    if (has_signal) *has_signal = s.mixflag[(size_t)r.second * e->n_mixers + mixer];
+    e->mix_fetched[mixer]++;
+    s.mix_pending--;
+    // drop queue entries every mixer has consumed
+    int mn = e->mix_fetched[0];
+    for (int v : e->mix_fetched) mn = std::min(mn, v);
+    while (mn > 0) {
+        e->mix_ready.pop_front();
+        for (int& v : e->mix_fetched) v--;
+        mn--;
+    }
+    return 1;
+}
+
+int abg_mixer_device_buffers(abg_engine* e, float** dev_sums, int32_t** dev_flags) {
+    if (e->n_mixers <= 0) return fail(ABG_EINVAL, "abg_mixer_device_buffers: no mixers configured");
+    if (dev_sums) *dev_sums = e->mix_sums.p;
+    if (dev_flags) *dev_flags = e->mix_flags.p;
+    return ABG_OK;
+}
+
+int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_debug_frame: device %d out of range", dev);
+    cudaSetDevice(e->cuda_dev);
+    Device& d = e->dev[dev];
+    Group& g = e->groups[d.group];
+    const int N = e->N;
+    unsigned char* raw = nullptr;
+    float2* spec = nullptr;
+    K1Dev* dk = nullptr;
+    const size_t bytes = (size_t)N * d.bpc;
+    CU(cudaMalloc((void**)&raw, bytes + 256));
+    CU(cudaMalloc((void**)&spec, sizeof(float2) * N));
+    CU(cudaMalloc((void**)&dk, sizeof(K1Dev)));
+    CU(cudaMemset(raw, 0, bytes + 256));
+    CU(cudaMemcpy(raw, iq_frame, bytes, cudaMemcpyHostToDevice));
+    K1Dev a{};
+    a.raw = raw; a.start_byte = 0; a.n_frames = 1; a.pos0 = 0; a.g0 = d.g0; a.n_channels = 0; a.hop_bytes = d.hop_bytes; a.sfmt = d.sfmt;
+    a.spec = spec; a.spec_first_pos = 0; a.wave_batch = e->B;
+    CU(cudaMemcpy(dk, &a, sizeof(a), cudaMemcpyHostToDevice));
+    K1Launch L{};
+    L.fft_size = N; L.n_devices = 1; L.max_frames = 1; L.frames_per_tile = g.frames_per_tile; L.tile_bytes_cap = g.tile_bytes_cap; L.devs = dk;
+    L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p; L.tw2 = e->tw2.p; L.win = e->win.p; L.iqin = e->iqin.p; L.Gp = e->Gp; L.sfmt = g.sfmt;
+    CU(cudaStreamSynchronize(e->stream));
+    cudaError_t er = abg_launch_k1(L, e->stream);
+    if (er != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er));
+    e->launches++;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(fftout, spec, sizeof(float2) * N, cudaMemcpyDeviceToHost));
+    cudaFree(raw); cudaFree(spec); cudaFree(dk);
+    return ABG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, driven through the C ABI, against the CPU oracle on the same
+seeded inputs, and against the committed golden fixtures.
+Gate: per audio sample |gpu - oracle| <= 1e-4 * max(1, |gpu|, |oracle|) — float32 path, tolerance
+1e-4 as north_star states — plus identical squelch decisions (axcindicate per batch, open/flap/CTCSS counters)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as op
+from airband_b200 import config as cm
+from airband_b200 import lib
+from airband_b200 import workloads as wl
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def gate(a, b, tol=TOL):
+    a = np.asarray(a); b = np.asarray(b)
+    err = np.abs(a - b) / np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    return float(err.max()) if err.size else 0.0
+
+
+def compare(cfg, raws, gres, geng, ores, oorc, tol=TOL):
+    for d in range(len(raws)):
+        gw, gi, ga = gres[d]
+        ow, oi, oa = ores[d]
+        assert gw.shape == ow.shape, (gw.shape, ow.shape)
+        assert np.array_equal(ga, oa), f"axcindicate differs on device {d}"
+        assert gate(gw, ow) <= tol, f"audio dev {d}: {gate(gw, ow)}"
+        assert gate(gi.real, oi.real) <= tol and gate(gi.imag, oi.imag) <= tol, f"iq_out dev {d}"
+        for c in range(gw.shape[0]):
+            gs, os_ = geng.stats(d, c), oorc.stats(d, c)
+            for f in ("open_count", "flappy_count", "ctcss_count", "no_ctcss_count", "active_counter", "dm_phi", "bin"):
+                assert getattr(gs, f) == getattr(os_, f), (d, c, f, getattr(gs, f), getattr(os_, f))
+            for f in ("noise_level", "signal_level", "squelch_level", "agcavgfast"):
+                a, b = getattr(gs, f), getattr(os_, f)
+                assert abs(a - b) <= 1e-4 * max(1.0, abs(a), abs(b)), (d, c, f, a, b)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_case_matches_oracle(name):
+    cfg, raws = CASES[name]()
+    ores, oorc = op.run_oracle(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws)
+    compare(cfg, raws, gres, geng, ores, oorc)
+
+
+@pytest.mark.parametrize("name", ["am_u8", "nfm_s16", "am_bw_f32"])
+def test_case_matches_golden_fixture(name):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    cfg, _ = CASES[name]()
+    raws = [g[f"raw{d}"] for d in range(len(cfg.devices))]
+    gres, geng = lib.demodulate_all(cfg, raws)
+    for d, (gw, gi, ga) in enumerate(gres):
+        assert np.array_equal(ga, g[f"axc{d}"])
+        assert gate(gw, g[f"waveout{d}"]) <= TOL
+        assert gate(gi.real, g[f"iq_out{d}"].real) <= TOL and gate(gi.imag, g[f"iq_out{d}"].imag) <= TOL
+        for c in range(gw.shape[0]):
+            s = geng.stats(d, c)
+            assert [s.open_count, s.flappy_count, s.ctcss_count, s.no_ctcss_count, s.active_counter] == list(g[f"counts{d}"][c])
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("sfmt", [cm.SFMT_U8, cm.SFMT_S8, cm.SFMT_S16, cm.SFMT_F32])
+def test_fft_stage_every_size_and_format(n, sfmt):
+    """conversion + window + FFT of one frame, full spectrum, vs the oracle's fftin->fftout for the same bytes."""
+    sr = 2560000
+    cfg = cm.Config(fft_size=n, wave_rate=8000,
+                    devices=[cm.Device(sample_rate=sr, sfmt=sfmt, centerfreq=0, channels=[cm.make_channel(100000, 0, sr, n, 8000)])])
+    raw = wl.synth_iq(cfg, 0, n, key_off_s=0.0, seed=n + sfmt, amplitude=0.3, noise_sigma=0.05)
+    o = op.Oracle(cfg)
+    _, ospec = o.debug_frame(0, raw)
+    e = lib.Engine(cfg)
+    gspec = e.debug_frame(0, raw)
+    scale = np.abs(ospec).max()
+    assert scale > 1.0
+    assert np.abs(gspec - ospec).max() / scale < 2e-6
+    # and against float64 numpy on the oracle's own float32 input (independent of the oracle's FFT)
+    fin, _ = o.debug_frame(0, raw)
+    ref = np.fft.fft(fin.astype(np.complex128))
+    assert np.abs(gspec - ref).max() / np.abs(ref).max() < 2e-6
+
+
+@pytest.mark.parametrize("nbmax", [1, 2, 4])
+def test_batches_per_run_do_not_change_results(nbmax):
+    cfg, raws = CASES["s8_two_devices"](n_batches=4)
+    ores, oorc = op.run_oracle(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws, max_batches_per_run=nbmax)
+    compare(cfg, raws, gres, geng, ores, oorc)
+
+
+def test_streaming_pushes_of_odd_sizes():
+    cfg, raws = CASES["am_u8"](n_batches=4)
+    ores, oorc = op.run_oracle(cfg, raws)
+    e = lib.Engine(cfg, max_batches_per_run=2, input_capacity_batches=3)
+    rng = np.random.default_rng(3)
+    pos, outs = 0, []
+    r = raws[0]
+    while pos < r.size or e.batches_available(0) > 0:
+        if pos < r.size:
+            step = 2 * int(rng.integers(1, 90000))
+            e.push(0, r[pos:pos + step])
+            pos += step
+        e.run(-1)
+        while True:
+            got = e.fetch(0)
+            if got is None:
+                break
+            outs.append(got)
+    gw = np.concatenate([x[0] for x in outs], 1)
+    assert gw.shape == ores[0][0].shape
+    assert gate(gw, ores[0][0]) <= TOL
+    assert np.array_equal(np.stack([x[2] for x in outs]), ores[0][2])
+
+
+def _small(cfg, nb, **kw):
+    raws = [wl.synth_iq(cfg, d, wl.samples_for_batches(cfg, d, nb), key_on_s=0.2, key_off_s=0.1, **kw) for d in range(len(cfg.devices))]
+    ores, oorc = op.run_oracle(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws)
+    compare(cfg, raws, gres, geng, ores, oorc)
+
+
+def test_cfg1_shape():
+    _small(wl.cfg1(two_channels=True), 5)
+
+
+def test_cfg2_shape_scaled_down():
+    _small(wl.cfg2(n_devices=3, n_channels=8), 3)
+
+
+@pytest.mark.parametrize("sfmt", [cm.SFMT_S16, cm.SFMT_F32])
+def test_cfg3_shape_scaled_down(sfmt):
+    _small(wl.cfg3(n_devices=1, n_channels=6, sfmt=sfmt, parity=True), 4)
+
+
+def test_cfg5_shape_scaled_down():
+    _small(wl.cfg5(n_devices=5, n_channels=8), 2)
+
+
+@pytest.mark.parametrize("n", [1024, 8192])
+def test_other_fft_sizes_end_to_end(n):
+    _small(wl.cfg2(n_devices=1, n_channels=4, fft_size=n), 2)
+
+
+def test_mixer_matches_reference_sum():
+    """cfg 4 shape: mixer m = sum over devices of channel m (reference src/mixer.cpp:133-140,189-214), mono and stereo."""
+    cfg = wl.cfg4()
+    nb = 3
+    raws = [wl.synth_iq(cfg, d, wl.samples_for_batches(cfg, d, nb), key_on_s=0.2, key_off_s=0.1) for d in range(len(cfg.devices))]
+    ores, _ = op.run_oracle(cfg, raws)
+    e = lib.Engine(cfg, max_batches_per_run=2)
+    mixers = [[(d, m, 1.0 + 0.25 * d, (-0.5 if (m == 1 and d == 0) else 0.0)) for d in range(len(cfg.devices))] for m in range(4)]
+    e.configure_mixers(mixers)
+    for d, r in enumerate(raws):
+        e.push(d, r)
+    got = {m: [] for m in range(4)}
+    while e.run(-1) > 0:
+        for d in range(len(raws)):
+            while e.fetch(d) is not None:
+                pass
+        for m in range(4):
+            while True:
+                r = e.fetch_mixer(m)
+                if r is None:
+                    break
+                got[m].append(r)
+    B = cfg.wave_batch
+    for m in range(4):
+        assert len(got[m]) == nb
+        for b in range(nb):
+            left = np.zeros(B, np.float32); right = np.zeros(B, np.float32); sig = False
+            for (d, c, amp, bal) in mixers[m]:
+                wo, _, ax = ores[d]
+                if ax[b, c] == ord(' '):
+                    continue
+                sig = True
+                ampl, ampr = np.float32(min(1.0, 1.0 - bal)), np.float32(min(1.0, 1.0 + bal))
+                x = wo[c, b * B:(b + 1) * B]
+                left = (left + x * (np.float32(amp) * ampl)).astype(np.float32)
+                right = (right + x * (np.float32(amp) * ampr)).astype(np.float32)
+            gl, gr, gs = got[m][b]
+            assert gs == sig
+            assert gate(gl, left) <= TOL and gate(gr, right) <= TOL
+
+
+def test_afc_follows_an_off_bin_carrier():
+    """AFC (reference src/rtl_airband.cpp:180-251): carrier 3 bins above the configured one; the bin must move up on the
+    squelch-open edge exactly as in the oracle, batch by batch."""
+    sr, n, w, cf = 2560000, 512, 8000, 120000000
+    ch = cm.make_channel(cf + 100000, cf, sr, n, w, squelch_dbfs=-40.0, afc=2)
+    ch.offset_hz = 100000.0 + 3 * (sr / n)  # transmit 3 bins high
+    cfg = cm.Config(fft_size=n, wave_rate=w, devices=[cm.Device(sample_rate=sr, sfmt=cm.SFMT_U8, centerfreq=cf, channels=[ch])])
+    raws = [wl.synth_iq(cfg, 0, wl.samples_for_batches(cfg, 0, 5), key_on_s=0.25, key_off_s=0.15, amplitude=0.3)]
+    ores, oorc = op.run_oracle(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws, max_batches_per_run=1)
+    assert np.any(ores[0][2] == ord('>')) or np.any(ores[0][2] == ord('<')), "oracle AFC never moved: case is not exercising AFC"
+    compare(cfg, raws, gres, geng, ores, oorc)
