@@ -261,6 +261,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         eng.run_resident(nb)
+    eng.join()  # main stream waits for the K2 stream: ev1 covers every kernel of every step
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)

@@ -131,6 +131,10 @@ ABG_API int abg_batches_available(const abg_engine* e, int dev);
 ABG_API int abg_run(abg_engine* e, int max_batches);
 /* Wait for everything enqueued so far. */
 ABG_API int abg_sync(abg_engine* e);
+/* Make the engine's main stream (see abg_set_stream) wait for all demodulation work enqueued so far, without blocking
+ * the host: a caller-side event recorded on that stream afterwards covers K1, K2 and the result copies.  (K2 runs on
+ * an internal second stream so that it overlaps the next run's K1.) */
+ABG_API int abg_join(abg_engine* e);
 
 /* Number of finished, unfetched batches of a device (the reference's dev->waveavail flag, one level deeper). */
 ABG_API int abg_batches_ready(abg_engine* e, int dev);

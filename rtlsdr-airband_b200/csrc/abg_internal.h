@@ -120,8 +120,10 @@ struct K2Launch {
     const K2Dev* devs;
     int32_t* bins;
     const int32_t* base_bins;
-    float* win;
+    float* win;               // [P][Gp] buffer K1 filled for THIS run
     float2* iqin;
+    float* win_next;          // buffer the next run's K1 fills: receives the AGC_EXTRA look-back rows
+    float2* iqin_next;
     float* wout;
     float2* iqout;            // may be null when no channel has I/Q outputs
     float* sqbuf;             // [102][Gp]

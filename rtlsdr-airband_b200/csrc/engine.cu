@@ -190,15 +190,20 @@ struct abg_engine {
     DevBuf<ChanParams> params;
     DevBuf<ChanState> state;
     DevBuf<int32_t> bins, base_bins;
-    DevBuf<float> win, wout, sqbuf, tone_coeff, tone_q1, tone_q2, tone_mag, lut;
-    DevBuf<float2> iqin, iqout, tw1, tw2;
+    DevBuf<float> win[2], wout, sqbuf, tone_coeff, tone_q1, tone_q2, tone_mag, lut;  // win/iqin are double-buffered: K1 of run i+1
+    DevBuf<float2> iqin[2], iqout, tw1, tw2;                                           // fills one while K2 of run i reads the other
     DevBuf<unsigned char> axc;
     K2Dev* d_k2 = nullptr;
     std::vector<K2Dev> h_k2;  // pageable staging (see Group::h_k1)
     std::vector<Slot> slots;
     int next_slot = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // stream A: ingest copies + K1
     bool own_stream = false;
+    cudaStream_t stream_b = nullptr; // stream B: K2, mixers, result copies, tail copy
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr};
+    cudaEvent_t tev_b[3] = {nullptr, nullptr, nullptr};  // stream B: before K2 / after K2 / end of run
+    uint64_t run_index = 0;
+    bool any_afc = false;
     uint64_t launches = 0;
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // run start / after K1 / after K2 / run end
     bool tev_valid = false;
@@ -212,11 +217,11 @@ struct abg_engine {
     std::deque<std::pair<int, int>> mix_ready;  // (slot, batch-in-run), same for every mixer
     std::vector<int> mix_fetched;               // per mixer: entries of mix_ready already popped by that mixer
 
-    K2Launch k2_launch() const {
+    K2Launch k2_launch(int cur) const {
         K2Launch L{};
         L.G = G; L.Gp = Gp; L.P = P; L.wave_batch = B; L.fm_demod = fm_demod; L.iq_stride = nbmax * B;
         L.params = params.p; L.state = state.p; L.devs = d_k2; L.bins = bins.p; L.base_bins = base_bins.p;
-        L.win = win.p; L.iqin = iqin.p; L.wout = wout.p; L.iqout = any_iq_out ? iqout.p : nullptr;
+        L.win = win[cur].p; L.iqin = iqin[cur].p; L.win_next = win[cur ^ 1].p; L.iqin_next = iqin[cur ^ 1].p; L.wout = wout.p; L.iqout = any_iq_out ? iqout.p : nullptr;
         L.sqbuf = sqbuf.p; L.tone_coeff = tone_coeff.p; L.tone_q1 = tone_q1.p; L.tone_q2 = tone_q2.p; L.tone_mag = tone_mag.p;
         L.axc = axc.p; L.sincos_lut = lut.p;
         return L;
@@ -229,6 +234,7 @@ void engine_free(abg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cuda_dev);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->stream_b) cudaStreamSynchronize(e->stream_b);
     for (auto& d : e->dev) {
         for (int i = 0; i < 2; i++)
             if (d.raw[i]) cudaFree(d.raw[i]);
@@ -239,8 +245,8 @@ void engine_free(abg_engine* e) {
         g.wsc.free();
         if (g.d_k1) cudaFree(g.d_k1);
     }
-    e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win.free(); e->wout.free(); e->sqbuf.free();
-    e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin.free(); e->iqout.free();
+    e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win[0].free(); e->win[1].free(); e->wout.free(); e->sqbuf.free();
+    e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin[0].free(); e->iqin[1].free(); e->iqout.free();
     e->tw1.free(); e->tw2.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
     if (e->d_k2) cudaFree(e->d_k2);
     for (auto& s : e->slots) {
@@ -253,6 +259,13 @@ void engine_free(abg_engine* e) {
     }
     for (auto& ev : e->tev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->tev_b)
+        if (ev) cudaEventDestroy(ev);
+    for (int k = 0; k < 2; k++) {
+        if (e->ev_k1[k]) cudaEventDestroy(e->ev_k1[k]);
+        if (e->ev_k2[k]) cudaEventDestroy(e->ev_k2[k]);
+    }
+    if (e->stream_b) cudaStreamDestroy(e->stream_b);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -461,6 +474,14 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     // ---- CUDA resources ----------------------------------------------------------------------------------------------------
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
+    CU(cudaStreamCreateWithFlags(&e->stream_b, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&e->ev_k1[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_k2[k], cudaEventDisableTiming));
+    }
+    for (auto& ev : e->tev_b) CU(cudaEventCreate(&ev));
+    for (auto& d : e->dev)
+        if (d.has_afc) e->any_afc = true;
     for (auto& g : e->groups) {
         g.frames_per_tile = abg_k1_tile_frames(N, g.sfmt, g.hop_bytes, &g.tile_bytes_cap);
         if (g.frames_per_tile < 1) return fail(ABG_EINVAL, "fft_size=%d with this sample format does not fit shared memory", N);
@@ -484,7 +505,7 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         if (d.has_afc) CU(cudaMalloc((void**)&d.spec, sizeof(float2) * (size_t)e->nbmax * N));
     }
     const size_t PG = (size_t)e->P * Gp;
-    if (e->params.alloc(Gp) || e->state.alloc(Gp) || e->bins.alloc(Gp) || e->base_bins.alloc(Gp) || e->win.alloc(PG) || e->iqin.alloc(PG) ||
+    if (e->params.alloc(Gp) || e->state.alloc(Gp) || e->bins.alloc(Gp) || e->base_bins.alloc(Gp) || e->win[0].alloc(PG) || e->win[1].alloc(PG) || e->iqin[0].alloc(PG) || e->iqin[1].alloc(PG) ||
         e->wout.alloc(PG) || e->sqbuf.alloc((size_t)ABG_SQ_BUF * Gp) || e->tone_coeff.alloc(h_coeff.size()) || e->tone_q1.alloc(h_coeff.size()) ||
         e->tone_q2.alloc(h_coeff.size()) || e->tone_mag.alloc(h_coeff.size()) || e->lut.alloc(h_lut.size()) || e->tw1.alloc(h_tw1.size()) ||
         e->tw2.alloc(std::max<size_t>(h_tw2.size(), 1)) || e->axc.alloc((size_t)e->nbmax * Gp) ||
@@ -502,7 +523,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     CU(cudaMemcpy(e->lut.p, h_lut.data(), sizeof(float) * h_lut.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->tw1.p, h_tw1.data(), sizeof(float2) * h_tw1.size(), cudaMemcpyHostToDevice));
     if (!h_tw2.empty()) CU(cudaMemcpy(e->tw2.p, h_tw2.data(), sizeof(float2) * h_tw2.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemset(e->iqin.p, 0, sizeof(float2) * PG));
+    CU(cudaMemset(e->iqin[0].p, 0, sizeof(float2) * PG));
+    CU(cudaMemset(e->iqin[1].p, 0, sizeof(float2) * PG));
     if (e->any_iq_out) CU(cudaMemset(e->iqout.p, 0, sizeof(float2) * (size_t)Gp * e->nbmax * B));
     {
         // config.cpp:313-316: wavein[0..AGC_EXTRA) = 20, waveout[0..AGC_EXTRA) = 0.5.  (wavein's priming values are
@@ -512,7 +534,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
             for (int g = 0; g < Gp; g++) hw[(size_t)k * Gp + g] = 20.0f;
         for (int g = 0; g < Gp; g++)
             for (int k = 0; k < ABG_AGC_EXTRA; k++) ho[(size_t)g * e->P + k] = 0.5f;
-        CU(cudaMemcpy(e->win.p, hw.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->win[0].p, hw.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->win[1].p, hw.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(e->wout.p, ho.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc((void**)&e->d_k2, sizeof(K2Dev) * e->dev.size()));
@@ -546,9 +569,15 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
             return fail(ABG_EOVERFLOW, "output overrun: %d finished batches not fetched yet", e->slots[slot].pending + e->slots[slot].mix_pending);
         e->next_slot = (e->next_slot + 1) % (int)e->slots.size();
     }
-    cudaStream_t st = e->stream;
-    CU(cudaEventRecord(e->tev[0], st));
-    // ---- K1 per group ----
+    cudaStream_t sa = e->stream, sb = e->stream_b;
+    const uint64_t ri = e->run_index;
+    const int cur = (int)(ri & 1);
+    // K1 of this run overwrites win/iqin[cur], last read by K2 of run ri-2; with AFC it also needs the bins K2 of
+    // run ri-1 chose.  (ev_k2[x] is re-recorded by every run of that parity; the wait binds to the latest record.)
+    if (ri >= 2) CU(cudaStreamWaitEvent(sa, e->ev_k2[cur], 0));
+    if (ri >= 1 && e->any_afc) CU(cudaStreamWaitEvent(sa, e->ev_k2[cur ^ 1], 0));
+    CU(cudaEventRecord(e->tev[0], sa));
+    // ---- K1 per group (stream A) ----
     for (auto& g : e->groups) {
         int max_frames = 0;
         for (size_t k = 0; k < g.devs.size(); k++) {
@@ -570,40 +599,43 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
             max_frames = std::max(max_frames, a.n_frames);
         }
         if (max_frames == 0) continue;
-        CU(cudaMemcpyAsync(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, sa));
         K1Launch L{};
         L.fft_size = N; L.n_devices = (int)g.devs.size(); L.max_frames = max_frames; L.frames_per_tile = g.frames_per_tile;
         L.tile_bytes_cap = g.tile_bytes_cap; L.devs = g.d_k1; L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p;
-        L.tw2 = e->tw2.p; L.win = e->win.p; L.iqin = e->iqin.p; L.Gp = e->Gp; L.sfmt = g.sfmt;
-        cudaError_t er = abg_launch_k1(L, st);
-        if (er != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er));
+        L.tw2 = e->tw2.p; L.win = e->win[cur].p; L.iqin = e->iqin[cur].p; L.Gp = e->Gp; L.sfmt = g.sfmt;
+        cudaError_t er1 = abg_launch_k1(L, sa);
+        if (er1 != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er1));
         e->launches++;
     }
-    CU(cudaEventRecord(e->tev[1], st));
-    // ---- K2 ----
+    CU(cudaEventRecord(e->tev[1], sa));
+    CU(cudaEventRecord(e->ev_k1[cur], sa));
+    // ---- K2 (stream B, after this run's K1; overlaps the next run's K1) ----
+    CU(cudaStreamWaitEvent(sb, e->ev_k1[cur], 0));
     for (size_t i = 0; i < e->dev.size(); i++) {
         e->h_k2[i].n_batches = nb[i];
         e->h_k2[i].fft_size = N;
         e->h_k2[i].spec = e->dev[i].has_afc ? e->dev[i].spec : nullptr;
     }
-    CU(cudaMemcpyAsync(e->d_k2, e->h_k2.data(), sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, st));
-    K2Launch L2 = e->k2_launch();
-    cudaError_t er = abg_launch_k2(L2, st);
+    CU(cudaMemcpyAsync(e->d_k2, e->h_k2.data(), sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, sb));
+    CU(cudaEventRecord(e->tev_b[0], sb));
+    K2Launch L2 = e->k2_launch(cur);
+    cudaError_t er = abg_launch_k2(L2, sb);
     if (er != cudaSuccess) return fail(ABG_ECUDA, "K2 launch failed: %s", cudaGetErrorString(er));
     e->launches++;
-    CU(cudaEventRecord(e->tev[2], st));
+    CU(cudaEventRecord(e->tev_b[1], sb));
     // ---- mixers: sums over the just-finished batches, before the tail copy (output.cpp:533-535 -> mixer.cpp) ----
     if (e->n_mixers > 0) {
         MixLaunch M{};
         M.n_mixers = e->n_mixers; M.n_batches = nbrun; M.wave_batch = B; M.P = e->P; M.Gp = e->Gp; M.offsets = e->mix_offsets.p;
         M.inputs = e->mix_inputs.p; M.devs = e->d_k2; M.wout = e->wout.p; M.axc = e->axc.p; M.sums = e->mix_sums.p; M.flags = e->mix_flags.p;
-        er = abg_launch_mix(M, st);
+        er = abg_launch_mix(M, sb);
         if (er != cudaSuccess) return fail(ABG_ECUDA, "mixer launch failed: %s", cudaGetErrorString(er));
         e->launches++;
         if (queue_outputs) {
             Slot& s = e->slots[slot];
-            CU(cudaMemcpyAsync(s.mix, e->mix_sums.p, sizeof(float) * (size_t)nbrun * e->n_mixers * 2 * B, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(s.mixflag, e->mix_flags.p, sizeof(int32_t) * (size_t)nbrun * e->n_mixers, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(s.mix, e->mix_sums.p, sizeof(float) * (size_t)nbrun * e->n_mixers * 2 * B, cudaMemcpyDeviceToHost, sb));
+            CU(cudaMemcpyAsync(s.mixflag, e->mix_flags.p, sizeof(int32_t) * (size_t)nbrun * e->n_mixers, cudaMemcpyDeviceToHost, sb));
         }
     }
     // ---- results: D2H into the pinned slot, then the consumer's tail copy on the device ----
@@ -611,18 +643,18 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         Slot& s = e->slots[slot];
         const size_t stride = (size_t)e->nbmax * B;
         CU(cudaMemcpy2DAsync(s.wout, stride * sizeof(float), e->wout.p, (size_t)e->P * sizeof(float), (size_t)nbrun * B * sizeof(float), e->G,
-                             cudaMemcpyDeviceToHost, st));
+                             cudaMemcpyDeviceToHost, sb));
         if (e->any_iq_out)
             CU(cudaMemcpy2DAsync(s.iqout, stride * sizeof(float2), e->iqout.p, stride * sizeof(float2), (size_t)nbrun * B * sizeof(float2), e->G,
-                                 cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(s.axc, e->axc.p, (size_t)nbrun * e->Gp, cudaMemcpyDeviceToHost, st));
+                                 cudaMemcpyDeviceToHost, sb));
+        CU(cudaMemcpyAsync(s.axc, e->axc.p, (size_t)nbrun * e->Gp, cudaMemcpyDeviceToHost, sb));
     }
-    er = abg_launch_k2_tail(L2, st);
+    er = abg_launch_k2_tail(L2, sb);
     if (er != cudaSuccess) return fail(ABG_ECUDA, "tail-copy launch failed: %s", cudaGetErrorString(er));
     e->launches++;
     if (queue_outputs) {
         Slot& s = e->slots[slot];
-        CU(cudaEventRecord(s.done, st));
+        CU(cudaEventRecord(s.done, sb));
         for (size_t i = 0; i < e->dev.size(); i++)
             for (int b = 0; b < nb[i]; b++) {
                 e->dev[i].ready.emplace_back(slot, b);
@@ -634,8 +666,10 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
                 s.mix_pending += e->n_mixers;
             }
     }
-    CU(cudaEventRecord(e->tev[3], st));
+    CU(cudaEventRecord(e->tev_b[2], sb));
+    CU(cudaEventRecord(e->ev_k2[cur], sb));
     e->tev_valid = true;
+    e->run_index++;
     // ---- bookkeeping ----
     for (size_t i = 0; i < e->dev.size(); i++) {
         if (nb[i] <= 0) continue;
@@ -747,6 +781,13 @@ int abg_run(abg_engine* e, int max_batches) {
 int abg_sync(abg_engine* e) {
     cudaSetDevice(e->cuda_dev);
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
+    return ABG_OK;
+}
+
+int abg_join(abg_engine* e) {
+    cudaSetDevice(e->cuda_dev);
+    if (e->run_index > 0) CU(cudaStreamWaitEvent(e->stream, e->ev_k2[(e->run_index - 1) & 1], 0));
     return ABG_OK;
 }
 
@@ -787,6 +828,7 @@ int abg_get_stats(abg_engine* e, int dev, int chan, abg_squelch_stats* out) {
     if (chan < 0 || chan >= d.C || !out) return fail(ABG_ERANGE, "abg_get_stats: channel %d out of range", chan);
     cudaSetDevice(e->cuda_dev);
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
     ChanState s;
     int32_t bin;
     CU(cudaMemcpy(&s, e->state.p + d.g0 + chan, sizeof(s), cudaMemcpyDeviceToHost));
@@ -817,6 +859,7 @@ int abg_set_bin(abg_engine* e, int dev, int chan, int bin) {
     if (chan < 0 || chan >= d.C) return fail(ABG_ERANGE, "abg_set_bin: channel %d out of range", chan);
     if (bin < 0 || bin >= e->N) return fail(ABG_EINVAL, "abg_set_bin: bin %d outside 0..%d", bin, e->N - 1);
     cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream_b));
     int32_t v = bin;
     CU(cudaMemcpyAsync(e->bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->base_bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
@@ -854,6 +897,7 @@ int abg_run_resident(abg_engine* e, int n_batches) {
 int abg_set_stream(abg_engine* e, void* cuda_stream) {
     cudaSetDevice(e->cuda_dev);
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
     if (e->own_stream) cudaStreamDestroy(e->stream);
     e->stream = (cudaStream_t)cuda_stream;
     e->own_stream = false;
@@ -865,11 +909,11 @@ uint64_t abg_launch_count(const abg_engine* e) { return e->launches; }
 int abg_last_run_times(abg_engine* e, float* ms4) {
     if (!e->tev_valid) return fail(ABG_EINVAL, "abg_last_run_times: no run yet");
     cudaSetDevice(e->cuda_dev);
-    CU(cudaEventSynchronize(e->tev[3]));
-    CU(cudaEventElapsedTime(&ms4[0], e->tev[0], e->tev[1]));
-    CU(cudaEventElapsedTime(&ms4[1], e->tev[1], e->tev[2]));
-    CU(cudaEventElapsedTime(&ms4[2], e->tev[2], e->tev[3]));
-    CU(cudaEventElapsedTime(&ms4[3], e->tev[0], e->tev[3]));
+    CU(cudaEventSynchronize(e->tev_b[2]));
+    CU(cudaEventElapsedTime(&ms4[0], e->tev[0], e->tev[1]));      // K1 on stream A
+    CU(cudaEventElapsedTime(&ms4[1], e->tev_b[0], e->tev_b[1]));  // K2 on stream B
+    CU(cudaEventElapsedTime(&ms4[2], e->tev_b[1], e->tev_b[2]));  // mixers + result copies + tail copy
+    CU(cudaEventElapsedTime(&ms4[3], e->tev[0], e->tev_b[2]));    // first K1 launch to end of run
     return ABG_OK;
 }
 
@@ -877,6 +921,7 @@ int abg_mixers_configure(abg_engine* e, int n_mixers, const int32_t* input_offse
     if (n_mixers < 0 || (n_mixers > 0 && (!input_offsets || !inputs))) return fail(ABG_EINVAL, "abg_mixers_configure: bad arguments");
     cudaSetDevice(e->cuda_dev);
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
     if (!e->mix_ready.empty()) return fail(ABG_EINVAL, "abg_mixers_configure: unfetched mixer batches pending");
     const int total = n_mixers ? input_offsets[n_mixers] : 0;
     std::vector<MixInput> mi(total);
@@ -967,8 +1012,9 @@ int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout)
     CU(cudaMemcpy(dk, &a, sizeof(a), cudaMemcpyHostToDevice));
     K1Launch L{};
     L.fft_size = N; L.n_devices = 1; L.max_frames = 1; L.frames_per_tile = g.frames_per_tile; L.tile_bytes_cap = g.tile_bytes_cap; L.devs = dk;
-    L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p; L.tw2 = e->tw2.p; L.win = e->win.p; L.iqin = e->iqin.p; L.Gp = e->Gp; L.sfmt = g.sfmt;
+    L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p; L.tw2 = e->tw2.p; L.win = e->win[0].p; L.iqin = e->iqin[0].p; L.Gp = e->Gp; L.sfmt = g.sfmt;
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
     cudaError_t er = abg_launch_k1(L, e->stream);
     if (er != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er));
     e->launches++;

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libairband_b200.so")
 # every symbol include/airband_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "abg_last_error", "abg_version", "abg_create", "abg_destroy", "abg_wave_batch", "abg_hop", "abg_push",
-    "abg_batches_available", "abg_run", "abg_sync", "abg_batches_ready", "abg_fetch_batch", "abg_get_stats", "abg_set_bin",
+    "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_get_stats", "abg_set_bin",
     "abg_resident_load", "abg_run_resident", "abg_set_stream", "abg_launch_count", "abg_mixers_configure",
     "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times",
 ]
@@ -69,6 +69,7 @@ def load():
     L.abg_batches_available.restype, L.abg_batches_available.argtypes = i, [vp, i]
     L.abg_run.restype, L.abg_run.argtypes = i, [vp, i]
     L.abg_sync.restype, L.abg_sync.argtypes = i, [vp]
+    L.abg_join.restype, L.abg_join.argtypes = i, [vp]
     L.abg_batches_ready.restype, L.abg_batches_ready.argtypes = i, [vp, i]
     L.abg_fetch_batch.restype, L.abg_fetch_batch.argtypes = i, [vp, i, vp, vp, vp]
     L.abg_get_stats.restype, L.abg_get_stats.argtypes = i, [vp, i, i, C.POINTER(CSquelchStats)]
@@ -138,6 +139,9 @@ class Engine:
 
     def sync(self) -> None:
         self._chk(self.L.abg_sync(self.h))
+
+    def join(self) -> None:
+        self._chk(self.L.abg_join(self.h))
 
     def batches_ready(self, dev: int) -> int:
         return self._chk(self.L.abg_batches_ready(self.h, dev))
