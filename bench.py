@@ -346,7 +346,7 @@ def main():
             traffic = None
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {"bound": "hbm", "kernel": "k1_fft_kernel (convert+window+FFT+bin select)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+    roofline = {"bound": "hbm", "kernel": ("k1_fft_kernel" if args.fft_mode == 1 else "k1_pruned_kernel") + " (convert+window+FFT+bin select)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6650 GB/s",
                 "traffic": traffic, "alg_bytes_per_launch": alg_bytes, "k1_ms": k1 * 1e3, "k2_ms": k2 * 1e3,
                 "k1_share_of_step": k1 / max(k1 + k2, 1e-12),

@@ -112,6 +112,9 @@ struct K1Launch {
 };
 cudaError_t abg_launch_k1(const K1Launch& L, cudaStream_t s);
 int abg_k1_tile_frames(int fft_size, int sfmt, int hop_bytes, int* tile_bytes_cap);
+// output-pruned variant (k1_pruned.cu): only the configured bins are evaluated in the last pass
+cudaError_t abg_launch_k1_pruned(const K1Launch& L, const float2* twn, int max_channels, cudaStream_t s);
+int abg_k1p_tile_frames(int fft_size, int sfmt, int hop_bytes, int max_channels, int* tile_bytes_cap);
 
 struct K2Launch {
     int G, Gp, P, wave_batch, fm_demod, iq_stride;  // iq_stride = nbmax * B

@@ -160,7 +160,10 @@ struct Group {
     int sfmt, hop_bytes;
     float fullscale;
     std::vector<int> devs;
-    int frames_per_tile = 0, tile_bytes_cap = 0;
+    int frames_per_tile = 0, tile_bytes_cap = 0;      // full-spectrum kernel (k1_fft.cu)
+    int p_frames_per_tile = 0, p_tile_bytes_cap = 0;  // output-pruned kernel (k1_pruned.cu)
+    int max_channels = 0;
+    bool pruned = false;                               // which kernel this group runs
     DevBuf<float> wsc;
     K1Dev* d_k1 = nullptr;  // device array [devs.size()]
     std::vector<K1Dev> h_k1;  // PAGEABLE staging on purpose: cudaMemcpyAsync snapshots pageable sources before returning
@@ -191,7 +194,7 @@ struct abg_engine {
     DevBuf<ChanState> state;
     DevBuf<int32_t> bins, base_bins;
     DevBuf<float> win[2], wout, sqbuf, tone_coeff, tone_q1, tone_q2, tone_mag, lut;  // win/iqin are double-buffered: K1 of run i+1
-    DevBuf<float2> iqin[2], iqout, tw1, tw2;                                           // fills one while K2 of run i reads the other
+    DevBuf<float2> iqin[2], iqout, tw1, tw2, twn;                                           // fills one while K2 of run i reads the other
     DevBuf<unsigned char> axc;
     K2Dev* d_k2 = nullptr;
     std::vector<K2Dev> h_k2;  // pageable staging (see Group::h_k1)
@@ -247,7 +250,7 @@ void engine_free(abg_engine* e) {
     }
     e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win[0].free(); e->win[1].free(); e->wout.free(); e->sqbuf.free();
     e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin[0].free(); e->iqin[1].free(); e->iqout.free();
-    e->tw1.free(); e->tw2.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
+    e->tw1.free(); e->tw2.free(); e->twn.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
     if (e->d_k2) cudaFree(e->d_k2);
     for (auto& s : e->slots) {
         if (s.wout) cudaFreeHost(s.wout);
@@ -451,6 +454,12 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
             }
     }
 
+    std::vector<float2> h_twn((size_t)N);
+    for (int m = 0; m < N; m++) {
+        double ang = -2.0 * M_PI * (double)m / (double)N;
+        h_twn[m] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+
     // ---- groups (one K1 launch per sample format / full-scale / hop) ------------------------------------------------------
     for (int i = 0; i < (int)e->dev.size(); i++) {
         Device& d = e->dev[i];
@@ -485,6 +494,14 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     for (auto& g : e->groups) {
         g.frames_per_tile = abg_k1_tile_frames(N, g.sfmt, g.hop_bytes, &g.tile_bytes_cap);
         if (g.frames_per_tile < 1) return fail(ABG_EINVAL, "fft_size=%d with this sample format does not fit shared memory", N);
+        bool group_afc = false;
+        for (int di : g.devs) {
+            g.max_channels = std::max(g.max_channels, e->dev[di].C);
+            if (e->dev[di].has_afc) group_afc = true;
+        }
+        g.p_frames_per_tile = abg_k1p_tile_frames(N, g.sfmt, g.hop_bytes, g.max_channels, &g.p_tile_bytes_cap);
+        // fft_mode: 0 auto = output-pruned last pass unless the group needs whole spectra (AFC); 1 = always full; 2 = pruned
+        g.pruned = (e->fft_mode != 1) && !group_afc && g.p_frames_per_tile >= 1;
         // window * 1/full-scale: U8 levels are (i-127.5)/127.5, S8 i/128 (rtl_airband.cpp:319-324); S16/F32 scale = 1/fullscale (:403,421)
         float scale = g.sfmt == ABG_SFMT_U8 ? 1.0f / 127.5f : g.sfmt == ABG_SFMT_S8 ? 1.0f / 128.0f : 1.0f / g.fullscale;
         std::vector<float> wsc(N);
@@ -508,7 +525,7 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     if (e->params.alloc(Gp) || e->state.alloc(Gp) || e->bins.alloc(Gp) || e->base_bins.alloc(Gp) || e->win[0].alloc(PG) || e->win[1].alloc(PG) || e->iqin[0].alloc(PG) || e->iqin[1].alloc(PG) ||
         e->wout.alloc(PG) || e->sqbuf.alloc((size_t)ABG_SQ_BUF * Gp) || e->tone_coeff.alloc(h_coeff.size()) || e->tone_q1.alloc(h_coeff.size()) ||
         e->tone_q2.alloc(h_coeff.size()) || e->tone_mag.alloc(h_coeff.size()) || e->lut.alloc(h_lut.size()) || e->tw1.alloc(h_tw1.size()) ||
-        e->tw2.alloc(std::max<size_t>(h_tw2.size(), 1)) || e->axc.alloc((size_t)e->nbmax * Gp) ||
+        e->tw2.alloc(std::max<size_t>(h_tw2.size(), 1)) || e->twn.alloc(h_twn.size()) || e->axc.alloc((size_t)e->nbmax * Gp) ||
         (e->any_iq_out && e->iqout.alloc((size_t)Gp * e->nbmax * B)))
         return fail(ABG_ENOMEM, "Out of device memory. Try fewer devices per GPU or a smaller max_batches_per_run.");
     CU(cudaMemcpy(e->params.p, hp.data(), sizeof(ChanParams) * Gp, cudaMemcpyHostToDevice));
@@ -523,6 +540,7 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     CU(cudaMemcpy(e->lut.p, h_lut.data(), sizeof(float) * h_lut.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->tw1.p, h_tw1.data(), sizeof(float2) * h_tw1.size(), cudaMemcpyHostToDevice));
     if (!h_tw2.empty()) CU(cudaMemcpy(e->tw2.p, h_tw2.data(), sizeof(float2) * h_tw2.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->twn.p, h_twn.data(), sizeof(float2) * h_twn.size(), cudaMemcpyHostToDevice));
     CU(cudaMemset(e->iqin[0].p, 0, sizeof(float2) * PG));
     CU(cudaMemset(e->iqin[1].p, 0, sizeof(float2) * PG));
     if (e->any_iq_out) CU(cudaMemset(e->iqout.p, 0, sizeof(float2) * (size_t)Gp * e->nbmax * B));
@@ -601,12 +619,14 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         if (max_frames == 0) continue;
         CU(cudaMemcpyAsync(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, sa));
         K1Launch L{};
-        L.fft_size = N; L.n_devices = (int)g.devs.size(); L.max_frames = max_frames; L.frames_per_tile = g.frames_per_tile;
-        L.tile_bytes_cap = g.tile_bytes_cap; L.devs = g.d_k1; L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p;
+        L.fft_size = N; L.n_devices = (int)g.devs.size(); L.max_frames = max_frames;
+        L.frames_per_tile = g.pruned ? g.p_frames_per_tile : g.frames_per_tile;
+        L.tile_bytes_cap = g.pruned ? g.p_tile_bytes_cap : g.tile_bytes_cap;
+        L.devs = g.d_k1; L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p;
         L.tw2 = e->tw2.p; L.win = e->win[cur].p; L.iqin = e->iqin[cur].p; L.Gp = e->Gp; L.sfmt = g.sfmt;
-        cudaError_t er1 = abg_launch_k1(L, sa);
+        cudaError_t er1 = g.pruned ? abg_launch_k1_pruned(L, e->twn.p, g.max_channels, sa) : abg_launch_k1(L, sa);
         if (er1 != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er1));
-        e->launches++;
+        e->launches += g.pruned ? (uint64_t)((g.max_channels + 31) / 32) : 1;
     }
     CU(cudaEventRecord(e->tev[1], sa));
     CU(cudaEventRecord(e->ev_k1[cur], sa));

@@ -40,11 +40,12 @@ def compare(cfg, raws, gres, geng, ores, oorc, tol=TOL):
                 assert abs(a - b) <= 1e-4 * max(1.0, abs(a), abs(b)), (d, c, f, a, b)
 
 
+@pytest.mark.parametrize("fft_mode", [1, 2], ids=["full_fft", "pruned_fft"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_case_matches_oracle(name):
+def test_case_matches_oracle(name, fft_mode):
     cfg, raws = CASES[name]()
     ores, oorc = op.run_oracle(cfg, raws)
-    gres, geng = lib.demodulate_all(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws, fft_mode=fft_mode)
     compare(cfg, raws, gres, geng, ores, oorc)
 
 
@@ -116,11 +117,13 @@ def test_streaming_pushes_of_odd_sizes():
     assert np.array_equal(np.stack([x[2] for x in outs]), ores[0][2])
 
 
-def _small(cfg, nb, **kw):
+def _small(cfg, nb, fft_modes=(1, 2), **kw):
     raws = [wl.synth_iq(cfg, d, wl.samples_for_batches(cfg, d, nb), key_on_s=0.2, key_off_s=0.1, **kw) for d in range(len(cfg.devices))]
     ores, oorc = op.run_oracle(cfg, raws)
-    gres, geng = lib.demodulate_all(cfg, raws)
-    compare(cfg, raws, gres, geng, ores, oorc)
+    for mode in fft_modes:  # 1 = full-spectrum kernel, 2 = output-pruned kernel
+        gres, geng = lib.demodulate_all(cfg, raws, fft_mode=mode)
+        compare(cfg, raws, gres, geng, ores, oorc)
+        geng.close()
 
 
 def test_cfg1_shape():
@@ -140,9 +143,30 @@ def test_cfg5_shape_scaled_down():
     _small(wl.cfg5(n_devices=5, n_channels=8), 2)
 
 
-@pytest.mark.parametrize("n", [1024, 8192])
+@pytest.mark.parametrize("n", [256, 1024, 8192])
 def test_other_fft_sizes_end_to_end(n):
     _small(wl.cfg2(n_devices=1, n_channels=4, fft_size=n), 2)
+
+
+def test_many_channels_per_device():
+    """49 channels on one device (config/big_mixer.conf has 49): exercises the pruned kernel's R1=16 path and its
+    32-channel passes."""
+    _small(wl.cfg2(n_devices=1, n_channels=49, fft_size=1024), 2)
+
+
+@pytest.mark.parametrize("n,sfmt", [(4096, cm.SFMT_F32), (512, cm.SFMT_S8), (2048, cm.SFMT_S16)])
+def test_pruned_equals_full_spectrum_bins(n, sfmt):
+    """The two K1 kernels must agree on the extracted bins far inside the audio gate (same inputs, 2 batches)."""
+    sr = 2560000
+    chans = [cm.make_channel(o, 0, sr, n, 8000, squelch_dbfs=-30.0, rawfile=True) for o in (-600000, -25000, 12500, 333000, 910000)]
+    cfg = cm.Config(fft_size=n, wave_rate=8000, devices=[cm.Device(sample_rate=sr, sfmt=sfmt, centerfreq=0, channels=chans)])
+    raws = [wl.synth_iq(cfg, 0, wl.samples_for_batches(cfg, 0, 2), key_off_s=0.0, amplitude=0.1)]
+    (fw, fi, fa), e1 = lib.demodulate_all(cfg, raws, fft_mode=1)[0][0], None
+    (pw, pi, pa), e2 = lib.demodulate_all(cfg, raws, fft_mode=2)[0][0], None
+    assert np.array_equal(fa, pa) and np.any(fa == ord('*'))
+    scale = np.abs(fi).max()
+    assert scale > 1.0 and np.abs(fi - pi).max() / scale < 3e-6
+    assert gate(fw, pw) <= 1e-5
 
 
 def test_mixer_matches_reference_sum():
