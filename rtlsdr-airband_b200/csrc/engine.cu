@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -207,6 +208,7 @@ struct abg_engine {
     cudaEvent_t tev_b[3] = {nullptr, nullptr, nullptr};  // stream B: before K2 / after K2 / end of run
     uint64_t run_index = 0;
     bool any_afc = false;
+    int k2_lpw = 32;
     uint64_t launches = 0;
     cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // run start / after K1 / after K2 / run end
     bool tev_valid = false;
@@ -223,6 +225,7 @@ struct abg_engine {
     K2Launch k2_launch(int cur) const {
         K2Launch L{};
         L.G = G; L.Gp = Gp; L.P = P; L.wave_batch = B; L.fm_demod = fm_demod; L.iq_stride = nbmax * B;
+        L.lanes_per_warp = k2_lpw;
         L.params = params.p; L.state = state.p; L.devs = d_k2; L.bins = bins.p; L.base_bins = base_bins.p;
         L.win = win[cur].p; L.iqin = iqin[cur].p; L.win_next = win[cur ^ 1].p; L.iqin_next = iqin[cur ^ 1].p; L.wout = wout.p; L.iqout = any_iq_out ? iqout.p : nullptr;
         L.sqbuf = sqbuf.p; L.tone_coeff = tone_coeff.p; L.tone_q1 = tone_q1.p; L.tone_q2 = tone_q2.p; L.tone_mag = tone_mag.p;
@@ -483,7 +486,12 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     // ---- CUDA resources ----------------------------------------------------------------------------------------------------
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
-    CU(cudaStreamCreateWithFlags(&e->stream_b, cudaStreamNonBlocking));
+    {
+        // K2's few long-running warps must get their SM slots ahead of the next run's K1 blocks
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&e->stream_b, cudaStreamNonBlocking, hi));
+    }
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&e->ev_k1[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->ev_k2[k], cudaEventDisableTiming));
@@ -491,6 +499,18 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     for (auto& ev : e->tev_b) CU(cudaEventCreate(&ev));
     for (auto& d : e->dev)
         if (d.has_afc) e->any_afc = true;
+    {
+        // K2 is a latency-bound sequential recurrence per channel: use as few channels per warp as keeps the warp count
+        // near a few per SM (less divergence between channels in different squelch states, more SMs in use)
+        int lpw = 1;
+        while (lpw < 32 && (e->G + lpw - 1) / lpw > 592) lpw <<= 1;
+        const char* env = getenv("ABG_K2_LPW");
+        if (env && atoi(env) > 0) {
+            lpw = 1;
+            while (lpw < 32 && lpw < atoi(env)) lpw <<= 1;
+        }
+        e->k2_lpw = lpw;
+    }
     for (auto& g : e->groups) {
         g.frames_per_tile = abg_k1_tile_frames(N, g.sfmt, g.hop_bytes, &g.tile_bytes_cap);
         if (g.frames_per_tile < 1) return fail(ABG_EINVAL, "fft_size=%d with this sample format does not fit shared memory", N);
