@@ -167,7 +167,10 @@ struct Group {
     bool pruned = false;                               // which kernel this group runs
     DevBuf<float> wsc;
     K1Dev* d_k1 = nullptr;  // device array [devs.size()]
-    std::vector<K1Dev> h_k1;  // PAGEABLE staging on purpose: cudaMemcpyAsync snapshots pageable sources before returning
+    // pinned staging ring (a pageable source would make cudaMemcpyAsync synchronise the stream first and serialise the
+    // K1/K2 pipeline); a slot is reused only after the copy that read it has completed (stage_done)
+    K1Dev* h_k1[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_done[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct Slot {
@@ -198,7 +201,8 @@ struct abg_engine {
     DevBuf<float2> iqin[2], iqout, tw1, tw2, twn;                                           // fills one while K2 of run i reads the other
     DevBuf<unsigned char> axc;
     K2Dev* d_k2 = nullptr;
-    std::vector<K2Dev> h_k2;  // pageable staging (see Group::h_k1)
+    K2Dev* h_k2[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring (see Group::h_k1)
+    cudaEvent_t k2_stage_done[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<Slot> slots;
     int next_slot = 0;
     cudaStream_t stream = nullptr;   // stream A: ingest copies + K1
@@ -250,11 +254,19 @@ void engine_free(abg_engine* e) {
     for (auto& g : e->groups) {
         g.wsc.free();
         if (g.d_k1) cudaFree(g.d_k1);
+        for (int k = 0; k < 4; k++) {
+            if (g.h_k1[k]) cudaFreeHost(g.h_k1[k]);
+            if (g.stage_done[k]) cudaEventDestroy(g.stage_done[k]);
+        }
     }
     e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win[0].free(); e->win[1].free(); e->wout.free(); e->sqbuf.free();
     e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin[0].free(); e->iqin[1].free(); e->iqout.free();
     e->tw1.free(); e->tw2.free(); e->twn.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
     if (e->d_k2) cudaFree(e->d_k2);
+    for (int k = 0; k < 4; k++) {
+        if (e->h_k2[k]) cudaFreeHost(e->h_k2[k]);
+        if (e->k2_stage_done[k]) cudaEventDestroy(e->k2_stage_done[k]);
+    }
     for (auto& s : e->slots) {
         if (s.wout) cudaFreeHost(s.wout);
         if (s.iqout) cudaFreeHost(s.iqout);
@@ -529,7 +541,10 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         CU(g.wsc.alloc(N));
         CU(cudaMemcpy(g.wsc.p, wsc.data(), N * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMalloc((void**)&g.d_k1, sizeof(K1Dev) * g.devs.size()));
-        g.h_k1.resize(g.devs.size());
+        for (int k = 0; k < 4; k++) {
+            CU(cudaMallocHost((void**)&g.h_k1[k], sizeof(K1Dev) * g.devs.size()));
+            CU(cudaEventCreateWithFlags(&g.stage_done[k], cudaEventDisableTiming));
+        }
     }
     for (auto& d : e->dev) {
         // room for in_cap_batches batches + the AGC_EXTRA priming frames + one window, + slack for 16-byte TMA rounding
@@ -577,7 +592,10 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         CU(cudaMemcpy(e->wout.p, ho.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc((void**)&e->d_k2, sizeof(K2Dev) * e->dev.size()));
-    e->h_k2.resize(e->dev.size());
+    for (int k = 0; k < 4; k++) {
+        CU(cudaMallocHost((void**)&e->h_k2[k], sizeof(K2Dev) * e->dev.size()));
+        CU(cudaEventCreateWithFlags(&e->k2_stage_done[k], cudaEventDisableTiming));
+    }
     e->slots.resize(3);
     for (auto& s : e->slots) {
         CU(cudaMallocHost((void**)&s.wout, sizeof(float) * (size_t)std::max(G, 1) * e->nbmax * B));
@@ -616,12 +634,14 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     if (ri >= 1 && e->any_afc) CU(cudaStreamWaitEvent(sa, e->ev_k2[cur ^ 1], 0));
     CU(cudaEventRecord(e->tev[0], sa));
     // ---- K1 per group (stream A) ----
+    const int stg = (int)(ri & 3);
     for (auto& g : e->groups) {
         int max_frames = 0;
+        if (ri >= 4) CU(cudaEventSynchronize(g.stage_done[stg]));
         for (size_t k = 0; k < g.devs.size(); k++) {
             const int di = g.devs[k];
             Device& d = e->dev[di];
-            K1Dev& a = g.h_k1[k];
+            K1Dev& a = g.h_k1[stg][k];
             const bool primed = resident ? d.res_primed : d.primed;
             a.raw = resident ? d.res : d.raw[d.cur];
             a.n_frames = nb[di] > 0 ? nb[di] * B + (primed ? 0 : ABG_AGC_EXTRA) : 0;
@@ -637,7 +657,8 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
             max_frames = std::max(max_frames, a.n_frames);
         }
         if (max_frames == 0) continue;
-        CU(cudaMemcpyAsync(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, sa));
+        CU(cudaMemcpyAsync(g.d_k1, g.h_k1[stg], sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, sa));
+        CU(cudaEventRecord(g.stage_done[stg], sa));
         K1Launch L{};
         L.fft_size = N; L.n_devices = (int)g.devs.size(); L.max_frames = max_frames;
         L.frames_per_tile = g.pruned ? g.p_frames_per_tile : g.frames_per_tile;
@@ -652,12 +673,14 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     CU(cudaEventRecord(e->ev_k1[cur], sa));
     // ---- K2 (stream B, after this run's K1; overlaps the next run's K1) ----
     CU(cudaStreamWaitEvent(sb, e->ev_k1[cur], 0));
+    if (ri >= 4) CU(cudaEventSynchronize(e->k2_stage_done[stg]));
     for (size_t i = 0; i < e->dev.size(); i++) {
-        e->h_k2[i].n_batches = nb[i];
-        e->h_k2[i].fft_size = N;
-        e->h_k2[i].spec = e->dev[i].has_afc ? e->dev[i].spec : nullptr;
+        e->h_k2[stg][i].n_batches = nb[i];
+        e->h_k2[stg][i].fft_size = N;
+        e->h_k2[stg][i].spec = e->dev[i].has_afc ? e->dev[i].spec : nullptr;
     }
-    CU(cudaMemcpyAsync(e->d_k2, e->h_k2.data(), sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, sb));
+    CU(cudaMemcpyAsync(e->d_k2, e->h_k2[stg], sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, sb));
+    CU(cudaEventRecord(e->k2_stage_done[stg], sb));
     CU(cudaEventRecord(e->tev_b[0], sb));
     K2Launch L2 = e->k2_launch(cur);
     cudaError_t er = abg_launch_k2(L2, sb);

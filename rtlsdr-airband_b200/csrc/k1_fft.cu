@@ -315,6 +315,7 @@ cudaError_t launch_one(const K1Launch& L, const K1Args& args, cudaStream_t s) {
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
     const int tiles = (L.max_frames + L.frames_per_tile - 1) / L.frames_per_tile;

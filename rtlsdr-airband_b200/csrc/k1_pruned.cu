@@ -245,6 +245,7 @@ cudaError_t pr_launch_one(const K1Launch& L, const PrArgs& args, cudaStream_t s)
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
     const int tiles = (L.max_frames + L.frames_per_tile - 1) / L.frames_per_tile;
