@@ -1,0 +1,117 @@
+// Host-side mirror of the reference structures the demodulation path touches, and the replacement thread function.
+//
+// The reference's own rtl_airband.h cannot be included here (it pulls lame/shout/libconfig++/fftw3 headers that are
+// not installed), so this header restates ONLY the fields demodulate() reads or writes, with the reference's names:
+//   input_t           reference src/input-common.h:39-57   (ring: buffer, buf_size, bufs, bufe, buffer_lock, state, sfmt ...)
+//   freq_t            reference src/rtl_airband.h:223-233  (the Squelch / filter objects appear as their config values)
+//   channel_t         reference src/rtl_airband.h:234-263
+//   device_t          reference src/rtl_airband.h:266-286
+//   demod_params_t    reference src/rtl_airband.h:310-320  (no FFTW plan: the engine owns the transform)
+//   Signal            reference src/rtl_airband.h:201-221
+// In the reference tree the WITH_B200 branch uses the real structs; this mirror exists so that the
+// adapter logic is compiled and tested in this repository.
+#pragma once
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/airband_b200.h"
+
+#define AGC_EXTRA 100  // reference src/rtl_airband.h:74
+
+typedef enum { SFMT_UNDEF = 0, SFMT_U8, SFMT_S8, SFMT_S16, SFMT_F32 } sample_format_t;  // input-common.h:31
+typedef enum { INPUT_UNKNOWN = 0, INPUT_INITIALIZED, INPUT_RUNNING, INPUT_FAILED, INPUT_STOPPED, INPUT_DISABLED } input_state_t;
+enum status { NO_SIGNAL = ' ', SIGNAL = '*', AFC_UP = '<', AFC_DOWN = '>' };  // rtl_airband.h:101
+enum modulations { MOD_AM, MOD_NFM };                                          // rtl_airband.h:193-199
+
+struct input_t {
+    unsigned char* buffer;  // buf_size + 2 * bytes_per_sample * fft_size bytes (wrap tail, input-helpers.cpp:27-36)
+    size_t buf_size, bufs, bufe;
+    size_t overflow_count;
+    input_state_t state;
+    sample_format_t sfmt;
+    float fullscale;
+    int bytes_per_sample;
+    int sample_rate;
+    int centerfreq;
+    pthread_mutex_t buffer_lock;
+};
+
+class Signal {  // rtl_airband.h:201-221
+   public:
+    Signal() {
+        pthread_cond_init(&cond_, NULL);
+        pthread_mutex_init(&mutex_, NULL);
+    }
+    void send() {
+        pthread_mutex_lock(&mutex_);
+        pthread_cond_signal(&cond_);
+        pthread_mutex_unlock(&mutex_);
+    }
+    void wait_ms(int ms);  // the reference waits without timeout; tests must not hang on a lost wake-up
+
+   private:
+    pthread_cond_t cond_;
+    pthread_mutex_t mutex_;
+};
+
+struct freq_t {
+    int frequency;
+    float agcavgfast;  // mirrored back from the engine for the stats file
+    float ampfactor;
+    size_t active_counter;
+    enum modulations modulation;
+    // what parse_channels() hands to Squelch / NotchFilter / LowpassFilter (config.cpp:437-619)
+    float squelch_level, squelch_snr_db, notch_hz, notch_q, ctcss_hz, lowpass_hz;
+    // Squelch getters the stats code reads (squelch.h:89-96)
+    float noise_level, signal_level, squelch_level_now;
+    size_t open_count, flappy_count, ctcss_count, no_ctcss_count;
+};
+
+struct channel_t {
+    float* waveout;  // [WAVE_LEN]; the consumer reads [0, WAVE_BATCH)
+    float* iq_out;   // [2 * WAVE_LEN]
+    float alpha;
+    uint32_t dm_dphi;
+    enum status axcindicate;
+    unsigned char afc;
+    freq_t* freqlist;
+    int freq_count, freq_idx;
+    int needs_raw_iq, has_iq_outputs;
+};
+
+struct device_t {
+    input_t* input;
+    int channel_count;
+    size_t *base_bins, *bins;
+    channel_t* channels;
+    int waveavail;
+    size_t output_overrun_count;
+};
+
+struct demod_params_t {
+    Signal* mp3_signal;
+    int device_start;
+    int device_end;
+};
+
+// process-wide state the reference keeps in globals (rtl_airband.cpp:71-90)
+struct b200_globals {
+    device_t* devices;
+    int device_count;
+    size_t fft_size;
+    int wave_rate;            // WAVE_RATE as a run-time value
+    int fm_demod;
+    volatile int do_exit;
+    volatile int devices_running;
+    int wait_for_consumer;    // offline use (file input faster than real time): deliver a batch only once waveavail == 0
+    int max_batches_per_run;
+    char last_error[512];
+};
+extern b200_globals g_b200;
+
+// Drop-in for `void* demodulate(void* params)` (reference src/rtl_airband.cpp:286, started at :1111).
+extern "C" ABG_API void* demodulate_b200(void* params);
+
+// circbuffer_append (reference src/input-helpers.cpp:37-63), used by the test feeder
+void circbuffer_append(input_t* const input, unsigned char* buf, size_t len);

@@ -1,0 +1,234 @@
+// Test harness around demodulate_b200(): builds devices[] / channels / input rings the way parse_devices() does
+// (reference src/config.cpp:793-815), runs one feeder thread per device that behaves like file_rx_thread()
+// (reference src/input-file.cpp:82-147: reads buf_size/2 - 1 bytes at a time, waits for ring space, flags
+// INPUT_FAILED at end of data), the demod thread under test, and a consumer that does what output_thread() does with a
+// finished batch (reference src/output.cpp:903-923: read waveout[0..WAVE_BATCH), clear waveavail).  Exposed through a
+// small C ABI so pytest can drive it.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "airband_host.h"
+
+#define MIN_BUF_SIZE 2560000  // reference src/rtl_airband.h:61
+
+namespace {
+struct Feeder {
+    input_t* input;
+    const unsigned char* data;
+    size_t len;
+};
+void* feeder_thread(void* p) {
+    Feeder* f = (Feeder*)p;
+    input_t* input = f->input;
+    const size_t buf_len = (input->buf_size / 2) - 1;
+    size_t pos = 0;
+    input->state = INPUT_RUNNING;
+    while (!g_b200.do_exit) {
+        if (pos >= f->len) {  // feof(): "hit end of file, disabling"
+            // let the demod thread drain the ring first (the reference drops what is left)
+            input->state = INPUT_FAILED;
+            break;
+        }
+        size_t space_left;
+        pthread_mutex_lock(&input->buffer_lock);
+        if (input->bufe >= input->bufs)
+            space_left = input->bufs + (input->buf_size - input->bufe);
+        else
+            space_left = input->bufs - input->bufe;
+        pthread_mutex_unlock(&input->buffer_lock);
+        if (space_left > buf_len) {
+            size_t n = std::min(buf_len, f->len - pos);
+            // keep whole complex samples per append so the consumer never sees half a sample at the ring end
+            const size_t bpc = 2 * (size_t)input->bytes_per_sample;
+            if (n < f->len - pos) n -= n % bpc;
+            circbuffer_append(input, const_cast<unsigned char*>(f->data + pos), n);
+            pos += n;
+        } else {
+            usleep(1000);
+        }
+    }
+    return NULL;
+}
+
+struct Harness {
+    std::vector<device_t> devs;
+    std::vector<input_t> inputs;
+    std::vector<std::vector<channel_t>> chans;
+    std::vector<std::vector<freq_t>> freqs;
+    std::vector<std::vector<size_t>> bins, base_bins;
+    std::vector<std::vector<float>> bufs_wave, bufs_iq;
+    std::vector<std::vector<unsigned char>> rings;
+    // results
+    std::vector<std::vector<float>> out_wave;   // per device: batches x C x B
+    std::vector<std::vector<float>> out_iq;     // per device: batches x C x 2B
+    std::vector<std::vector<char>> out_axc;     // per device: batches x C
+    std::vector<int> n_batches;
+    int B = 0, wave_len = 0;
+    Signal sig;
+};
+struct Consumer {
+    Harness* h;
+    volatile int stop;
+};
+void consume_ready(Harness* h) {
+    for (size_t i = 0; i < h->devs.size(); i++) {
+        device_t* dev = &h->devs[i];
+        if (!dev->waveavail) continue;
+        for (int c = 0; c < dev->channel_count; c++) {
+            channel_t* ch = dev->channels + c;
+            h->out_wave[i].insert(h->out_wave[i].end(), ch->waveout, ch->waveout + h->B);
+            h->out_iq[i].insert(h->out_iq[i].end(), ch->iq_out, ch->iq_out + 2 * h->B);
+            h->out_axc[i].push_back((char)ch->axcindicate);
+        }
+        h->n_batches[i]++;
+        dev->waveavail = 0;  // output.cpp:922 (the AGC_EXTRA tail copy of :920 is done inside the engine)
+    }
+}
+void* consumer_thread(void* p) {
+    Consumer* c = (Consumer*)p;
+    while (!c->stop) {
+        c->h->sig.wait_ms(5);
+        consume_ready(c->h);
+    }
+    consume_ready(c->h);
+    return NULL;
+}
+}  // namespace
+
+extern "C" {
+
+ABG_API void* abh_create(const abg_config* cfg, int max_batches_per_run) {
+    Harness* h = new Harness();
+    const int D = cfg->n_devices;
+    h->B = cfg->wave_rate / 8;
+    h->wave_len = 2 * h->B + AGC_EXTRA;
+    h->devs.resize(D); h->inputs.resize(D); h->chans.resize(D); h->freqs.resize(D); h->bins.resize(D); h->base_bins.resize(D);
+    h->bufs_wave.resize(D); h->bufs_iq.resize(D); h->rings.resize(D);
+    h->out_wave.resize(D); h->out_iq.resize(D); h->out_axc.resize(D); h->n_batches.assign(D, 0);
+    memset(&g_b200, 0, sizeof(g_b200));
+    g_b200.fft_size = cfg->fft_size;
+    g_b200.wave_rate = cfg->wave_rate;
+    g_b200.fm_demod = cfg->fm_demod;
+    g_b200.wait_for_consumer = 1;
+    g_b200.max_batches_per_run = max_batches_per_run;
+    for (int i = 0; i < D; i++) {
+        const abg_device_cfg& dc = cfg->devices[i];
+        input_t& in = h->inputs[i];
+        memset(&in, 0, sizeof(in));
+        in.sfmt = (sample_format_t)dc.sfmt;
+        in.fullscale = dc.fullscale;
+        in.bytes_per_sample = dc.sfmt == ABG_SFMT_S16 ? 2 : (dc.sfmt == ABG_SFMT_F32 ? 4 : 1);
+        in.sample_rate = dc.sample_rate;
+        // config.cpp:793-803: MIN_BUF_SIZE rounded up to a multiple of one hop (ceil variant), + the wrap tail
+        size_t fft_batch_len = 2 * in.bytes_per_sample * (size_t)ceil((double)dc.sample_rate / (double)cfg->wave_rate);
+        in.buf_size = MIN_BUF_SIZE;
+        if (in.buf_size % fft_batch_len != 0) in.buf_size += fft_batch_len - in.buf_size % fft_batch_len;
+        h->rings[i].assign(in.buf_size + 2 * in.bytes_per_sample * (size_t)cfg->fft_size, 0);
+        in.buffer = h->rings[i].data();
+        in.state = INPUT_INITIALIZED;
+        pthread_mutex_init(&in.buffer_lock, NULL);
+        const int C = dc.n_channels;
+        h->chans[i].resize(C); h->freqs[i].resize(C); h->bins[i].resize(C); h->base_bins[i].resize(C);
+        h->bufs_wave[i].assign((size_t)C * h->wave_len, 0.0f);
+        h->bufs_iq[i].assign((size_t)C * 2 * h->wave_len, 0.0f);
+        for (int c = 0; c < C; c++) {
+            const abg_channel_cfg& cc = dc.channels[c];
+            channel_t& ch = h->chans[i][c];
+            freq_t& f = h->freqs[i][c];
+            memset(&ch, 0, sizeof(ch));
+            memset(&f, 0, sizeof(f));
+            ch.waveout = &h->bufs_wave[i][(size_t)c * h->wave_len];
+            ch.iq_out = &h->bufs_iq[i][(size_t)c * 2 * h->wave_len];
+            ch.alpha = cc.alpha;
+            ch.dm_dphi = cc.dm_dphi;
+            ch.axcindicate = NO_SIGNAL;
+            ch.afc = (unsigned char)cc.afc;
+            ch.freqlist = &f;
+            ch.freq_count = 1;
+            ch.needs_raw_iq = cc.needs_raw_iq;
+            ch.has_iq_outputs = cc.has_iq_outputs;
+            f.agcavgfast = 0.5f;
+            f.ampfactor = cc.ampfactor;
+            f.modulation = cc.modulation == ABG_MOD_NFM ? MOD_NFM : MOD_AM;
+            f.squelch_level = cc.squelch_level; f.squelch_snr_db = cc.squelch_snr_db; f.notch_hz = cc.notch_hz; f.notch_q = cc.notch_q;
+            f.ctcss_hz = cc.ctcss_hz; f.lowpass_hz = cc.lowpass_hz;
+            h->bins[i][c] = h->base_bins[i][c] = (size_t)cc.bin;
+        }
+        device_t& d = h->devs[i];
+        memset(&d, 0, sizeof(d));
+        d.input = &in;
+        d.channel_count = C;
+        d.bins = h->bins[i].data();
+        d.base_bins = h->base_bins[i].data();
+        d.channels = h->chans[i].data();
+    }
+    g_b200.devices = h->devs.data();
+    g_b200.device_count = D;
+    g_b200.devices_running = D;
+    return h;
+}
+
+// feed one raw stream per device through the rings, demodulate with demodulate_b200(), consume; returns 0 on success
+ABG_API int abh_run(void* hp, const unsigned char* const* raws, const size_t* raw_bytes, int timeout_s) {
+    Harness* h = (Harness*)hp;
+    const int D = (int)h->devs.size();
+    std::vector<Feeder> feeders(D);
+    std::vector<pthread_t> fth(D);
+    for (int i = 0; i < D; i++) {
+        feeders[i] = {&h->inputs[i], raws[i], raw_bytes[i]};
+        pthread_create(&fth[i], NULL, feeder_thread, &feeders[i]);
+    }
+    for (int t = 0; t < 5000; t++) {  // "wait for INPUT_RUNNING", rtl_airband.cpp:1024-1032
+        bool all = true;
+        for (int i = 0; i < D; i++) all = all && h->inputs[i].state != INPUT_INITIALIZED;
+        if (all) break;
+        usleep(1000);
+    }
+    demod_params_t dp = {&h->sig, 0, D};
+    pthread_t dth, cth;
+    Consumer cons = {h, 0};
+    pthread_create(&cth, NULL, consumer_thread, &cons);
+    pthread_create(&dth, NULL, demodulate_b200, &dp);
+    // finished when every feeder has ended, every ring is (nearly) empty and nothing new arrived for a while
+    int idle_ms = 0, last_total = -1, waited_ms = 0;
+    while (!g_b200.do_exit && waited_ms < timeout_s * 1000) {
+        usleep(20 * 1000);
+        waited_ms += 20;
+        bool fed = true;
+        for (int i = 0; i < D; i++) fed = fed && (h->inputs[i].state == INPUT_FAILED || h->inputs[i].state == INPUT_DISABLED);
+        int total = 0;
+        for (int i = 0; i < D; i++) total += h->n_batches[i];
+        if (fed && total == last_total)
+            idle_ms += 20;
+        else
+            idle_ms = 0;
+        last_total = total;
+        if (fed && idle_ms >= 400) break;
+    }
+    const bool timed_out = waited_ms >= timeout_s * 1000;
+    g_b200.do_exit = 1;
+    pthread_join(dth, NULL);
+    cons.stop = 1;
+    pthread_join(cth, NULL);
+    for (int i = 0; i < D; i++) pthread_join(fth[i], NULL);
+    if (g_b200.last_error[0]) return -2;
+    return timed_out ? -1 : 0;
+}
+
+ABG_API int abh_batches(void* hp, int dev) { return ((Harness*)hp)->n_batches[dev]; }
+ABG_API const float* abh_waveout(void* hp, int dev) { return ((Harness*)hp)->out_wave[dev].data(); }
+ABG_API const float* abh_iq_out(void* hp, int dev) { return ((Harness*)hp)->out_iq[dev].data(); }
+ABG_API const char* abh_axc(void* hp, int dev) { return ((Harness*)hp)->out_axc[dev].data(); }
+ABG_API size_t abh_overflows(void* hp, int dev) { return ((Harness*)hp)->inputs[dev].overflow_count; }
+ABG_API size_t abh_overruns(void* hp, int dev) { return ((Harness*)hp)->devs[dev].output_overrun_count; }
+ABG_API size_t abh_active_counter(void* hp, int dev, int chan) { return ((Harness*)hp)->freqs[dev][chan].active_counter; }
+ABG_API const char* abh_last_error(void) { return g_b200.last_error; }
+ABG_API void abh_destroy(void* hp) { delete (Harness*)hp; }
+
+}  // extern "C"

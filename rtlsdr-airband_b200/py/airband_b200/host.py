@@ -1,0 +1,67 @@
+"""ctypes driver of the C++ host adapter test harness (rtlsdr-airband_b200/host): input rings + demodulate_b200() +
+an output-thread stand-in, i.e. the reference's thread structure around the B200 engine."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List
+
+import numpy as np
+
+from .config import CConfig, Config
+from .lib import LIB_DIR
+
+HOST_LIB = os.path.join(LIB_DIR, "libairband_host.so")
+HOST_SYMBOLS = ["demodulate_b200", "b200_refresh_stats", "abh_create", "abh_run", "abh_batches", "abh_waveout", "abh_iq_out", "abh_axc",
+                "abh_overflows", "abh_overruns", "abh_active_counter", "abh_last_error", "abh_destroy"]
+_L = None
+
+
+def load():
+    global _L
+    if _L is None:
+        if not os.path.exists(HOST_LIB):
+            raise FileNotFoundError(f"{HOST_LIB} not found: run `make -C {LIB_DIR}`")
+        L = C.CDLL(HOST_LIB)
+        vp, i = C.c_void_p, C.c_int
+        L.abh_create.restype, L.abh_create.argtypes = vp, [C.POINTER(CConfig), i]
+        L.abh_run.restype, L.abh_run.argtypes = i, [vp, C.POINTER(vp), C.POINTER(C.c_size_t), i]
+        L.abh_batches.restype, L.abh_batches.argtypes = i, [vp, i]
+        for f in ("abh_waveout", "abh_iq_out", "abh_axc"):
+            getattr(L, f).restype, getattr(L, f).argtypes = vp, [vp, i]
+        L.abh_overflows.restype, L.abh_overflows.argtypes = C.c_size_t, [vp, i]
+        L.abh_overruns.restype, L.abh_overruns.argtypes = C.c_size_t, [vp, i]
+        L.abh_active_counter.restype, L.abh_active_counter.argtypes = C.c_size_t, [vp, i, i]
+        L.abh_last_error.restype, L.abh_last_error.argtypes = C.c_char_p, []
+        L.abh_destroy.restype, L.abh_destroy.argtypes = None, [vp]
+        _L = L
+    return _L
+
+
+def run_host_pipeline(cfg: Config, raws: List[np.ndarray], max_batches_per_run: int = 2, timeout_s: int = 120):
+    """Feed `raws` through input rings into demodulate_b200() and collect what the output thread would see.
+    Returns per device (waveout[C, nb*B], iq_out[C, nb*B] complex64, axc[nb, C], info dict)."""
+    L = load()
+    ccfg, keep = cfg.to_c()
+    h = L.abh_create(C.byref(ccfg), max_batches_per_run)
+    raws = [np.ascontiguousarray(r) for r in raws]
+    ptrs = (C.c_void_p * len(raws))(*[r.ctypes.data for r in raws])
+    sizes = (C.c_size_t * len(raws))(*[r.nbytes for r in raws])
+    rc = L.abh_run(h, ptrs, sizes, timeout_s)
+    if rc != 0:
+        msg = L.abh_last_error().decode()
+        L.abh_destroy(h)
+        raise RuntimeError(f"host pipeline failed rc={rc}: {msg}")
+    B = cfg.wave_batch
+    out = []
+    for d in range(len(raws)):
+        Cn = len(cfg.devices[d].channels)
+        nb = L.abh_batches(h, d)
+        wo = np.ctypeslib.as_array(C.cast(L.abh_waveout(h, d), C.POINTER(C.c_float)), shape=(nb, Cn, B)).copy() if nb else np.zeros((0, Cn, B), np.float32)
+        iq = np.ctypeslib.as_array(C.cast(L.abh_iq_out(h, d), C.POINTER(C.c_float)), shape=(nb, Cn, 2 * B)).copy() if nb else np.zeros((0, Cn, 2 * B), np.float32)
+        ax = np.ctypeslib.as_array(C.cast(L.abh_axc(h, d), C.POINTER(C.c_uint8)), shape=(nb, Cn)).copy() if nb else np.zeros((0, Cn), np.uint8)
+        info = {"overflows": int(L.abh_overflows(h, d)), "overruns": int(L.abh_overruns(h, d)),
+                "active": [int(L.abh_active_counter(h, d, c)) for c in range(Cn)]}
+        out.append((wo.transpose(1, 0, 2).reshape(Cn, nb * B), iq.transpose(1, 0, 2).reshape(Cn, nb * 2 * B).view(np.complex64), ax, info))
+    L.abh_destroy(h)
+    return out

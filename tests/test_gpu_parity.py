@@ -222,3 +222,23 @@ def test_afc_follows_an_off_bin_carrier():
     gres, geng = lib.demodulate_all(cfg, raws, max_batches_per_run=1)
     assert np.any(ores[0][2] == ord('>')) or np.any(ores[0][2] == ord('<')), "oracle AFC never moved: case is not exercising AFC"
     compare(cfg, raws, gres, geng, ores, oorc)
+
+
+def test_host_adapter_thread_function_matches_oracle():
+    """demodulate_b200() (the reference's demod thread contract: input rings with wrap tail, locking, waveavail +
+    Signal hand-shake) over the C ABI, fed like file_rx_thread() feeds it, vs the oracle on the same bytes.  The stream is
+    longer than one ring (2.56 MB) so the ring wraps."""
+    from airband_b200 import host
+    cfg, _ = CASES["s8_two_devices"]()
+    nb = 7
+    raws = [wl.synth_iq(cfg, d, wl.samples_for_batches(cfg, d, nb), key_on_s=0.2, key_off_s=0.1) for d in range(2)]
+    assert raws[1].nbytes > 2 * 2560000
+    ores, oorc = op.run_oracle(cfg, raws)
+    hres = host.run_host_pipeline(cfg, raws)
+    for d in range(2):
+        gw, gi, ga, info = hres[d]
+        ow, oi, oa = ores[d]
+        assert gw.shape == ow.shape and np.array_equal(ga, oa)
+        assert gate(gw, ow) <= TOL
+        assert info["overflows"] == 0 and info["overruns"] == 0
+        assert info["active"] == [int(np.sum(oa[:, c] != ord(' '))) for c in range(ow.shape[0])]

@@ -79,3 +79,10 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in text and "libairband_oracle" not in text and "airband_oracle.h" not in text, os.path.join(dirpath, f)
+
+
+def test_host_adapter_library_exports():
+    from airband_b200 import host
+    L = host.load()
+    for name in host.HOST_SYMBOLS:
+        assert hasattr(L, name), name
