@@ -19,6 +19,7 @@
 // using the full-spectrum kernel.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/airband_b200.h"
 #include "abg_internal.h"
@@ -30,6 +31,7 @@ using namespace k1;
 constexpr int PR_WARPS = 4;          // warps (= frames in flight) per CTA
 constexpr int PR_MAXCH = 32;         // channels handled per pass of the kernel
 constexpr int PR_PAD = 33;           // padded row length of the partial-sum matrix
+
 
 struct PrArgs {
     const K1Dev* devs;
@@ -58,7 +60,7 @@ __device__ __forceinline__ float2 load_sample_pr(const unsigned char* tile, int 
     }
 }
 
-template <int LOGN, int SFMT, int R1>
+template <int LOGN, int SFMT, int R1, int PR_GELEM>
 __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a) {
     constexpr int N = 1 << LOGN;
     constexpr int E = N / 32;                  // samples per lane
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
     constexpr int NCOL = E / R1;               // columns per lane
     constexpr int M1 = N / R1;                 // columns per frame
     constexpr int PAIR = NCOL >= 2 ? 2 : 1;    // adjacent columns owned by one lane
-    constexpr int GELEM = 32;                  // complex values held in registers at once (per lane)
+    constexpr int GELEM = PR_GELEM;            // complex values held in registers at once (per lane)
     constexpr int GCOL = (NCOL * R1 > GELEM) ? (GELEM / R1 >= PAIR ? GELEM / R1 : PAIR) : NCOL;  // columns per register group
     constexpr int NGRP = NCOL / GCOL;
     constexpr int BPC = bytes_per_cplx<SFMT>();
@@ -237,10 +239,10 @@ int pr_cm(int max_channels) {  // channels per pass: multiple of 4, at most PR_M
     return cm < 4 ? 4 : (cm > PR_MAXCH ? PR_MAXCH : cm);
 }
 
-template <int LOGN, int SFMT, int R1>
-cudaError_t pr_launch_one(const K1Launch& L, const PrArgs& args, cudaStream_t s) {
+template <int LOGN, int SFMT, int R1, int GE>
+cudaError_t pr_launch_one2(const K1Launch& L, const PrArgs& args, cudaStream_t s) {
     const size_t smem = pr_fixed_smem(1 << LOGN, R1, args.nchmax) + (size_t)L.tile_bytes_cap;
-    auto kern = k1_pruned_kernel<LOGN, SFMT, R1>;
+    auto kern = k1_pruned_kernel<LOGN, SFMT, R1, GE>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -252,6 +254,19 @@ cudaError_t pr_launch_one(const K1Launch& L, const PrArgs& args, cudaStream_t s)
     dim3 grid(tiles, L.n_devices, 1), block(PR_WARPS * 32, 1, 1);
     kern<<<grid, block, smem, s>>>(args);
     return cudaGetLastError();
+}
+
+template <int LOGN, int SFMT, int R1>
+cudaError_t pr_launch_one(const K1Launch& L, const PrArgs& args, cudaStream_t s) {
+    // registers per lane: 64 complex values at once (one pass over the channels per frame) when the frame has that many
+    // per lane, else 32; ABG_K1_GELEM=32 forces the smaller group (more resident warps, two passes over the channels)
+    static int ge = 0;
+    if (ge == 0) {
+        const char* e = getenv("ABG_K1_GELEM");
+        ge = (e && atoi(e) == 32) ? 32 : 64;
+    }
+    if (ge == 32) return pr_launch_one2<LOGN, SFMT, R1, 32>(L, args, s);
+    return pr_launch_one2<LOGN, SFMT, R1, 64>(L, args, s);
 }
 
 template <int LOGN, int R1>
@@ -279,7 +294,9 @@ int abg_k1p_tile_frames(int fft_size, int sfmt, int hop_bytes, int max_channels,
     const int bpc = (sfmt == ABG_SFMT_U8 || sfmt == ABG_SFMT_S8) ? 2 : (sfmt == ABG_SFMT_S16 ? 4 : 8);
     const size_t fixed = pr_fixed_smem(fft_size, r1, pr_cm(max_channels));
     const size_t frame_bytes = (size_t)fft_size * bpc;
-    size_t budget = 56 * 1024 > fixed + frame_bytes + 64 ? 56 * 1024 - fixed : frame_bytes + 64;
+    size_t per_cta = 56 * 1024;
+    if (const char* e = getenv("ABG_K1_CTA_KB")) per_cta = (size_t)atoi(e) * 1024;
+    size_t budget = per_cta > fixed + frame_bytes + 64 ? per_cta - fixed : frame_bytes + 64;
     if (fixed + budget > 220 * 1024) return -1;
     int tf = 1;
     if (budget > frame_bytes + 64) tf = 1 + (int)((budget - frame_bytes - 64) / (size_t)hop_bytes);
