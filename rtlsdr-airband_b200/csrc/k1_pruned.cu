@@ -21,6 +21,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/airband_b200.h"
 #include "abg_internal.h"
 #include "k1_common.cuh"
@@ -31,6 +33,7 @@ using namespace k1;
 constexpr int PR_WARPS = 4;          // warps (= frames in flight) per CTA
 constexpr int PR_MAXCH = 32;         // channels handled per pass of the kernel
 constexpr int PR_PAD = 33;           // padded row length of the partial-sum matrix
+constexpr int PR_FEW = 8;            // up to this many channels per device: partial sums accumulate in registers
 
 
 struct PrArgs {
@@ -57,6 +60,21 @@ __device__ __forceinline__ float2 load_sample_pr(const unsigned char* tile, int 
         return make_float2(i, q);
     } else {
         return load_sample<SFMT>(tile, byte_off);
+    }
+}
+
+// two adjacent samples (n, n+1); for 8-bit formats one 32-bit shared load when the pair is 4-byte aligned
+template <int SFMT, bool AL4>
+__device__ __forceinline__ void load_pair_pr(const unsigned char* tile, int byte_off, float2& x0, float2& x1) {
+    if constexpr (SFMT == ABG_SFMT_U8 && AL4) {
+        const unsigned int u = *reinterpret_cast<const unsigned int*>(tile + byte_off);
+        x0.x = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7604)) - 32895.5f;
+        x0.y = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614)) - 32895.5f;
+        x1.x = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7624)) - 32895.5f;
+        x1.y = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7634)) - 32895.5f;
+    } else {
+        x0 = load_sample_pr<SFMT>(tile, byte_off);
+        x1 = load_sample_pr<SFMT>(tile, byte_off + bytes_per_cplx<SFMT>());
     }
 }
 
@@ -121,6 +139,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
     mbar_wait0(mbar);
 
     float* part = s_part + warp * (2 * CM * PR_PAD);
+    const bool few = CM <= PR_FEW;  // launch-uniform
     const float* __restrict__ wsc = a.wsc;
     const int iters = (nf + PR_WARPS - 1) / PR_WARPS;
     for (int it = 0; it < iters; ++it) {
@@ -128,42 +147,46 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
         if (fl >= nf) break;  // warp-uniform
         const int fo = pre + fl * dv.hop_bytes;
         const int pos = dv.pos0 + f0 + fl;
+        float accr[PR_FEW], acci[PR_FEW];
+#pragma unroll
+        for (int c = 0; c < PR_FEW; ++c) accr[c] = acci[c] = 0.0f;
 
 #pragma unroll 1
         for (int grp = 0; grp < NGRP; ++grp) {
             // ---- load + convert + window: GCOL columns of R1 samples ----
             float2 v[GCOL][R1];
+            auto load_group = [&](auto al4_tag) {
+                constexpr bool AL4 = decltype(al4_tag)::value;
 #pragma unroll
-            for (int jj = 0; jj < GCOL; jj += PAIR) {
-                const int j = grp * GCOL + jj;
-                const int c0 = PAIR * lane + (PAIR * 32) * (j / PAIR);     // first column of the pair
+                for (int jj = 0; jj < GCOL; jj += PAIR) {
+                    const int j = grp * GCOL + jj;
+                    const int c0 = PAIR * lane + (PAIR * 32) * (j / PAIR);     // first column of the pair
 #pragma unroll
-                for (int n1 = 0; n1 < R1; ++n1) {
-                    const int n = c0 + M1 * n1;
-                    if constexpr (PAIR == 2) {
-                        const float2 w2 = __ldg(reinterpret_cast<const float2*>(wsc + n));
-                        const float2 x0 = load_sample_pr<SFMT>(tile, fo + n * BPC);
-                        const float2 x1 = load_sample_pr<SFMT>(tile, fo + (n + 1) * BPC);
-                        v[jj][n1] = make_float2(x0.x * w2.x, x0.y * w2.x);
-                        v[jj + 1][n1] = make_float2(x1.x * w2.y, x1.y * w2.y);
-                    } else {
-                        const float w = __ldg(wsc + n);
-                        const float2 x0 = load_sample_pr<SFMT>(tile, fo + n * BPC);
-                        v[jj][n1] = make_float2(x0.x * w, x0.y * w);
+                    for (int n1 = 0; n1 < R1; ++n1) {
+                        const int n = c0 + M1 * n1;
+                        if constexpr (PAIR == 2) {
+                            const float2 w2 = __ldg(reinterpret_cast<const float2*>(wsc + n));
+                            float2 x0, x1;
+                            load_pair_pr<SFMT, AL4>(tile, fo + n * BPC, x0, x1);
+                            v[jj][n1] = make_float2(x0.x * w2.x, x0.y * w2.x);
+                            v[jj + 1][n1] = make_float2(x1.x * w2.y, x1.y * w2.y);
+                        } else {
+                            const float w = __ldg(wsc + n);
+                            const float2 x0 = load_sample_pr<SFMT>(tile, fo + n * BPC);
+                            v[jj][n1] = make_float2(x0.x * w, x0.y * w);
+                        }
                     }
                 }
-            }
+            };
+            if (SFMT == ABG_SFMT_U8 && PAIR == 2 && (fo & 3) == 0)  // frame start 4-byte aligned in the tile (always, for even hops)
+                load_group(std::true_type{});
+            else
+                load_group(std::false_type{});
             // ---- R1-point FFT of every column (result row k in v[col][brev(k)]) ----
 #pragma unroll
             for (int jj = 0; jj < GCOL; ++jj) reg_fft<R1>(v[jj]);
 
             // ---- per channel: lane-partial of the dot product over this group's columns ----
-#pragma unroll 1
-            for (int c = 0; c < nch; ++c) {
-                const int row = s_k1[c];  // warp-uniform
-                const float2* U = s_U + c * NCOL + grp * GCOL;
-                float sr = 0.0f, si = 0.0f;
-                switch (row) {
 #define PR_CASE(R)                                                                   \
     case R: {                                                                        \
         _Pragma("unroll") for (int jj = 0; jj < GCOL; ++jj) {                        \
@@ -175,26 +198,61 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
             si = fmaf(y.y, u.x, si);                                                 \
         }                                                                            \
     } break;
-                    PR_CASE(0) PR_CASE(1) PR_CASE(2) PR_CASE(3) PR_CASE(4) PR_CASE(5) PR_CASE(6) PR_CASE(7)
-                    default:
-                        if constexpr (R1 == 16) {
-                            switch (row) {
-                                PR_CASE(8) PR_CASE(9) PR_CASE(10) PR_CASE(11) PR_CASE(12) PR_CASE(13) PR_CASE(14) PR_CASE(15)
-                                default: break;
-                            }
-                        }
-                        break;
-#undef PR_CASE
+#define PR_ROW_SWITCH()                                                                                   \
+    switch (row) {                                                                                        \
+        PR_CASE(0) PR_CASE(1) PR_CASE(2) PR_CASE(3) PR_CASE(4) PR_CASE(5) PR_CASE(6) PR_CASE(7)           \
+        default:                                                                                          \
+            if constexpr (R1 == 16) {                                                                     \
+                switch (row) {                                                                            \
+                    PR_CASE(8) PR_CASE(9) PR_CASE(10) PR_CASE(11) PR_CASE(12) PR_CASE(13) PR_CASE(14) PR_CASE(15) \
+                    default: break;                                                                       \
+                }                                                                                         \
+            }                                                                                             \
+            break;                                                                                        \
+    }
+            if (few) {
+                // up to PR_FEW channels: partial sums stay in registers across the groups (channel loop unrolled so that
+                // the accumulators are statically indexed); the per-lane factor is applied once, after the last group
+#pragma unroll
+                for (int c = 0; c < PR_FEW; ++c) {
+                    if (c < nch) {
+                        const int row = s_k1[c];  // warp-uniform
+                        const float2* U = s_U + c * NCOL + grp * GCOL;
+                        float sr = accr[c], si = acci[c];
+                        PR_ROW_SWITCH()
+                        accr[c] = sr;
+                        acci[c] = si;
+                    }
                 }
-                // times the per-lane factor W^(PAIR*lane*b)
-                const float2 bf = s_base[c * 32 + lane];
-                const float tr = fmaf(sr, bf.x, -si * bf.y), ti = fmaf(sr, bf.y, si * bf.x);
-                if (NGRP == 1 || grp == 0) {
-                    part[(2 * c) * PR_PAD + lane] = tr;
-                    part[(2 * c + 1) * PR_PAD + lane] = ti;
-                } else {
-                    part[(2 * c) * PR_PAD + lane] += tr;
-                    part[(2 * c + 1) * PR_PAD + lane] += ti;
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c) {
+                    const int row = s_k1[c];  // warp-uniform
+                    const float2* U = s_U + c * NCOL + grp * GCOL;
+                    float sr = 0.0f, si = 0.0f;
+                    PR_ROW_SWITCH()
+                    // times the per-lane factor W^(PAIR*lane*b)
+                    const float2 bf = s_base[c * 32 + lane];
+                    const float tr = fmaf(sr, bf.x, -si * bf.y), ti = fmaf(sr, bf.y, si * bf.x);
+                    if (NGRP == 1 || grp == 0) {
+                        part[(2 * c) * PR_PAD + lane] = tr;
+                        part[(2 * c + 1) * PR_PAD + lane] = ti;
+                    } else {
+                        part[(2 * c) * PR_PAD + lane] += tr;
+                        part[(2 * c + 1) * PR_PAD + lane] += ti;
+                    }
+                }
+            }
+#undef PR_ROW_SWITCH
+#undef PR_CASE
+        }
+        if (few) {
+#pragma unroll
+            for (int c = 0; c < PR_FEW; ++c) {
+                if (c < nch) {
+                    const float2 bf = s_base[c * 32 + lane];
+                    part[(2 * c) * PR_PAD + lane] = fmaf(accr[c], bf.x, -acci[c] * bf.y);
+                    part[(2 * c + 1) * PR_PAD + lane] = fmaf(accr[c], bf.y, acci[c] * bf.x);
                 }
             }
         }
