@@ -281,7 +281,9 @@ def main():
     # ---- e2e: host buffers through the public API (push H2D + run + fetch D2H) ----
     e2e = None
     if not args.no_e2e:
-        eng2 = lib.Engine(cfg, cuda_device=local_rank, max_batches_per_run=nb, input_capacity_batches=nb + 1, fft_mode=args.fft_mode)
+        # software-pipelined like any streaming user of the API: the input of step i+1 is pushed (H2D on the engine's
+        # ingest stream) before the results of step i are fetched, so copies and kernels of neighbouring steps overlap
+        eng2 = lib.Engine(cfg, cuda_device=local_rank, max_batches_per_run=nb, input_capacity_batches=2 * nb + 1, fft_mode=args.fft_mode)
         step_items = [nb * B * hop[d] * 2 for d in range(D)]          # array items per step per device
         prime_items = [(100 * hop[d] + cfg.fft_size) * 2 for d in range(D)]
         pinned = []
@@ -293,7 +295,7 @@ def main():
         ax = [np.empty(len(cfg.devices[d].channels), np.uint8) for d in range(D)]
         item = [cfg.devices[d].bytes_per_sample for d in range(D)]
 
-        def e2e_step(first: bool):
+        def submit(first: bool):
             for d in range(D):
                 base = pinned[d].data_ptr()
                 if first:
@@ -302,20 +304,25 @@ def main():
                     eng2.push_ptr(d, base + prime_items[d] * item[d], step_items[d] * item[d])
             n = eng2.run(nb)
             assert n == D * nb, (n, D * nb)
+
+        def collect():
             for d in range(D):
                 for _ in range(nb):
                     assert eng2.fetch_into(d, wo[d], ax[d])
 
-        e2e_step(True)
+        submit(True)
         for _ in range(max(args.warmup, 1)):
-            e2e_step(False)
+            submit(False)
+            collect()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_step(False)
+            submit(False)   # step i+1 in flight ...
+            collect()       # ... while step i's results are fetched (every step's input and output cross PCIe in here)
         eng2.sync()
         barrier()
         dt = time.perf_counter() - t0
+        collect()
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

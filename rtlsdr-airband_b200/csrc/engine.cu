@@ -149,6 +149,7 @@ struct Device {
     unsigned char* raw[2] = {nullptr, nullptr};
     int cur = 0;
     size_t cap = 0, fill = 0, consumed = 0;
+    int runs_since_compaction = 1;  // K1 launches that read raw[cur] since the last compaction
     // resident replay stream
     unsigned char* res = nullptr;
     size_t res_bytes = 0;
@@ -208,6 +209,9 @@ struct abg_engine {
     cudaStream_t stream = nullptr;   // stream A: ingest copies + K1
     bool own_stream = false;
     cudaStream_t stream_b = nullptr; // stream B: K2, mixers, result copies, tail copy
+    cudaStream_t stream_c = nullptr; // stream C: ingest (abg_push host->device copies, buffer compaction)
+    cudaEvent_t ev_ingest = nullptr; // last ingest operation
+    bool ingest_dirty = false;
     cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr};
     cudaEvent_t tev_b[3] = {nullptr, nullptr, nullptr};  // stream B: before K2 / after K2 / end of run
     uint64_t run_index = 0;
@@ -284,6 +288,11 @@ void engine_free(abg_engine* e) {
         if (e->ev_k2[k]) cudaEventDestroy(e->ev_k2[k]);
     }
     if (e->stream_b) cudaStreamDestroy(e->stream_b);
+    if (e->stream_c) {
+        cudaStreamSynchronize(e->stream_c);
+        cudaStreamDestroy(e->stream_c);
+    }
+    if (e->ev_ingest) cudaEventDestroy(e->ev_ingest);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -509,6 +518,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         CU(cudaEventCreateWithFlags(&e->ev_k2[k], cudaEventDisableTiming));
     }
     for (auto& ev : e->tev_b) CU(cudaEventCreate(&ev));
+    CU(cudaStreamCreateWithFlags(&e->stream_c, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_ingest, cudaEventDisableTiming));
     for (auto& d : e->dev)
         if (d.has_afc) e->any_afc = true;
     {
@@ -632,6 +643,11 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     // run ri-1 chose.  (ev_k2[x] is re-recorded by every run of that parity; the wait binds to the latest record.)
     if (ri >= 2) CU(cudaStreamWaitEvent(sa, e->ev_k2[cur], 0));
     if (ri >= 1 && e->any_afc) CU(cudaStreamWaitEvent(sa, e->ev_k2[cur ^ 1], 0));
+    if (!resident && e->ingest_dirty) {  // K1 reads what abg_push copied on the ingest stream
+        CU(cudaEventRecord(e->ev_ingest, e->stream_c));
+        CU(cudaStreamWaitEvent(sa, e->ev_ingest, 0));
+        e->ingest_dirty = false;
+    }
     CU(cudaEventRecord(e->tev[0], sa));
     // ---- K1 per group (stream A) ----
     const int stg = (int)(ri & 3);
@@ -743,6 +759,7 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
             const int frames = nb[i] * B + (d.primed ? 0 : ABG_AGC_EXTRA);
             d.consumed += (size_t)frames * d.hop_bytes;
             d.primed = true;
+            d.runs_since_compaction++;
         }
     }
     return ABG_OK;
@@ -803,19 +820,28 @@ int abg_push(abg_engine* e, int dev, const void* iq, size_t nbytes) {
     if (nbytes % d.bpc) return fail(ABG_EINVAL, "abg_push: %zu bytes is not a whole number of complex samples", nbytes);
     cudaSetDevice(e->cuda_dev);
     if (d.fill + nbytes > d.cap) {
-        // compact: move the unconsumed tail to the front of the other buffer (stream-ordered after any running K1).
-        // keep 16-byte alignment of the frame origin irrelevant: K1 aligns each tile itself.
+        // compact: move the unconsumed tail to the front of the other buffer.  Ingest runs on its own stream so that
+        // host->device copies overlap K1; the other buffer may still be read by the most recent K1, so wait for it.
         const size_t keep_from = d.consumed & ~(size_t)15;  // keep the copy 16-byte aligned on both sides
         const size_t rem = d.fill - keep_from;
         if (rem + nbytes > d.cap) {
             return fail(ABG_EOVERFLOW, "abg_push: device %d input buffer overflow (%zu buffered + %zu new > %zu)", dev, d.fill - d.consumed, nbytes, d.cap);
         }
-        CU(cudaMemcpyAsync(d.raw[d.cur ^ 1], d.raw[d.cur] + keep_from, rem, cudaMemcpyDeviceToDevice, e->stream));
+        // the destination buffer was last read by a K1 launched before the previous compaction: with at least one run since
+        // then that is run_index-2 or older, so the copy overlaps the K1 that is reading the current buffer right now
+        if (d.runs_since_compaction >= 1) {
+            if (e->run_index >= 2) CU(cudaStreamWaitEvent(e->stream_c, e->ev_k1[(e->run_index - 2) & 1], 0));
+        } else if (e->run_index >= 1) {
+            CU(cudaStreamWaitEvent(e->stream_c, e->ev_k1[(e->run_index - 1) & 1], 0));
+        }
+        d.runs_since_compaction = 0;
+        CU(cudaMemcpyAsync(d.raw[d.cur ^ 1], d.raw[d.cur] + keep_from, rem, cudaMemcpyDeviceToDevice, e->stream_c));
         d.cur ^= 1;
         d.fill = rem;
         d.consumed -= keep_from;
     }
-    CU(cudaMemcpyAsync(d.raw[d.cur] + d.fill, iq, nbytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d.raw[d.cur] + d.fill, iq, nbytes, cudaMemcpyHostToDevice, e->stream_c));
+    e->ingest_dirty = true;
     d.fill += nbytes;
     return ABG_OK;
 }
@@ -843,6 +869,7 @@ int abg_run(abg_engine* e, int max_batches) {
 
 int abg_sync(abg_engine* e) {
     cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream_c));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaStreamSynchronize(e->stream_b));
     return ABG_OK;

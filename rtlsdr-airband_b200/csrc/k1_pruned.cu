@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
     mbar_wait0(mbar);
 
     float* part = s_part + warp * (2 * CM * PR_PAD);
-    const bool few = CM <= PR_FEW;  // launch-uniform
+    // register-resident accumulators for <= PR_FEW channels were measured SLOWER on B200 (0.618 vs 0.541 ms on cfg2:
+    // 102 registers and a much larger unrolled body); the path is kept for reference but compiled out
+    constexpr bool few = false;
     const float* __restrict__ wsc = a.wsc;
     const int iters = (nf + PR_WARPS - 1) / PR_WARPS;
     for (int it = 0; it < iters; ++it) {
