@@ -155,6 +155,15 @@ struct MixLaunch {
     const unsigned char* axc; // [nbmax][Gp]
     float* sums;              // [nbmax][n_mixers][2][B]
     int32_t* flags;           // [nbmax][n_mixers]
+    float* host_sums;         // same layout in the pinned result slot, or null
+    int32_t* host_flags;
 };
 cudaError_t abg_launch_mix(const MixLaunch& L, cudaStream_t s);
-cudaError_t abg_launch_k2_tail(const K2Launch& L, cudaStream_t s);
+// host-visible (pinned, mapped) result slot the end-of-run kernel writes; all null = no export (resident benchmark runs)
+struct K2Export {
+    float* host_wout;          // [G][stride]
+    float2* host_iqout;        // [G][stride] or null
+    unsigned char* host_axc;   // [nbmax][Gp]
+    size_t stride;             // nbmax * WAVE_BATCH
+};
+cudaError_t abg_launch_k2_tail(const K2Launch& L, const K2Export& X, cudaStream_t s);

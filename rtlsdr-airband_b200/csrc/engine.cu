@@ -708,28 +708,25 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         MixLaunch M{};
         M.n_mixers = e->n_mixers; M.n_batches = nbrun; M.wave_batch = B; M.P = e->P; M.Gp = e->Gp; M.offsets = e->mix_offsets.p;
         M.inputs = e->mix_inputs.p; M.devs = e->d_k2; M.wout = e->wout.p; M.axc = e->axc.p; M.sums = e->mix_sums.p; M.flags = e->mix_flags.p;
+        if (queue_outputs) {
+            M.host_sums = e->slots[slot].mix;
+            M.host_flags = e->slots[slot].mixflag;
+        }
         er = abg_launch_mix(M, sb);
         if (er != cudaSuccess) return fail(ABG_ECUDA, "mixer launch failed: %s", cudaGetErrorString(er));
         e->launches++;
-        if (queue_outputs) {
-            Slot& s = e->slots[slot];
-            CU(cudaMemcpyAsync(s.mix, e->mix_sums.p, sizeof(float) * (size_t)nbrun * e->n_mixers * 2 * B, cudaMemcpyDeviceToHost, sb));
-            CU(cudaMemcpyAsync(s.mixflag, e->mix_flags.p, sizeof(int32_t) * (size_t)nbrun * e->n_mixers, cudaMemcpyDeviceToHost, sb));
-        }
     }
-    // ---- results: D2H into the pinned slot, then the consumer's tail copy on the device ----
+    // ---- results: the end-of-run kernel writes them straight into the pinned slot, then does the consumer's tail copy ----
+    K2Export X{};
     if (queue_outputs) {
         Slot& s = e->slots[slot];
-        const size_t stride = (size_t)e->nbmax * B;
-        CU(cudaMemcpy2DAsync(s.wout, stride * sizeof(float), e->wout.p, (size_t)e->P * sizeof(float), (size_t)nbrun * B * sizeof(float), e->G,
-                             cudaMemcpyDeviceToHost, sb));
-        if (e->any_iq_out)
-            CU(cudaMemcpy2DAsync(s.iqout, stride * sizeof(float2), e->iqout.p, stride * sizeof(float2), (size_t)nbrun * B * sizeof(float2), e->G,
-                                 cudaMemcpyDeviceToHost, sb));
-        CU(cudaMemcpyAsync(s.axc, e->axc.p, (size_t)nbrun * e->Gp, cudaMemcpyDeviceToHost, sb));
+        X.host_wout = s.wout;
+        X.host_iqout = e->any_iq_out ? reinterpret_cast<float2*>(s.iqout) : nullptr;
+        X.host_axc = s.axc;
+        X.stride = (size_t)e->nbmax * B;
     }
-    er = abg_launch_k2_tail(L2, sb);
-    if (er != cudaSuccess) return fail(ABG_ECUDA, "tail-copy launch failed: %s", cudaGetErrorString(er));
+    er = abg_launch_k2_tail(L2, X, sb);
+    if (er != cudaSuccess) return fail(ABG_ECUDA, "export/tail-copy launch failed: %s", cudaGetErrorString(er));
     e->launches++;
     if (queue_outputs) {
         Slot& s = e->slots[slot];
