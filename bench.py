@@ -291,8 +291,8 @@ def main():
             need = prime_items[d] + step_items[d]
             src = torch.from_numpy(np.ascontiguousarray(raws[d][:need])).pin_memory()
             pinned.append(src)
-        wo = [np.empty((len(cfg.devices[d].channels), B), np.float32) for d in range(D)]
-        ax = [np.empty(len(cfg.devices[d].channels), np.uint8) for d in range(D)]
+        wo = [np.empty((nb, len(cfg.devices[d].channels), B), np.float32) for d in range(D)]
+        ax = [np.empty((nb, len(cfg.devices[d].channels)), np.uint8) for d in range(D)]
         item = [cfg.devices[d].bytes_per_sample for d in range(D)]
 
         def submit(first: bool):
@@ -307,8 +307,7 @@ def main():
 
         def collect():
             for d in range(D):
-                for _ in range(nb):
-                    assert eng2.fetch_into(d, wo[d], ax[d])
+                assert eng2.fetch_many_into(d, nb, wo[d], ax[d]) == nb
 
         submit(True)
         for _ in range(max(args.warmup, 1)):

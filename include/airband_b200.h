@@ -143,6 +143,9 @@ ABG_API int abg_batches_ready(abg_engine* e, int dev);
  * AGC_EXTRA tail copy at output.cpp:920, which the engine performs itself), iq_out[C][2*WAVE_BATCH] (may be NULL),
  * axcindicate[C].  Returns 1 if a batch was popped, 0 if none is ready, < 0 on error.  Synchronises as needed. */
 ABG_API int abg_fetch_batch(abg_engine* e, int dev, float* waveout, float* iq_out, char* axcindicate);
+/* Same for up to max_batches finished batches of one device in one call: waveout[n][C][WAVE_BATCH], iq_out[n][C][2*WAVE_BATCH]
+ * (may be NULL), axcindicate[n][C].  Returns the number of batches popped. */
+ABG_API int abg_fetch_batches(abg_engine* e, int dev, int max_batches, float* waveout, float* iq_out, char* axcindicate);
 
 ABG_API int abg_get_stats(abg_engine* e, int dev, int chan, abg_squelch_stats* out);
 /* Retune a channel's bin between batches: scan mode (controller_thread, reference src/rtl_airband.cpp:101-139) or an

@@ -909,6 +909,21 @@ int abg_fetch_batch(abg_engine* e, int dev, float* waveout, float* iq_out, char*
     return 1;
 }
 
+int abg_fetch_batches(abg_engine* e, int dev, int max_batches, float* waveout, float* iq_out, char* axcindicate) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_fetch_batches: device %d out of range", dev);
+    const Device& d = e->dev[dev];
+    const size_t C = (size_t)d.C, B = (size_t)e->B;
+    int n = 0;
+    while (n < max_batches) {
+        int rc = abg_fetch_batch(e, dev, waveout ? waveout + (size_t)n * C * B : nullptr, iq_out ? iq_out + (size_t)n * C * 2 * B : nullptr,
+                                 axcindicate ? axcindicate + (size_t)n * C : nullptr);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+        n++;
+    }
+    return n;
+}
+
 int abg_get_stats(abg_engine* e, int dev, int chan, abg_squelch_stats* out) {
     if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_get_stats: device %d out of range", dev);
     Device& d = e->dev[dev];

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libairband_b200.so")
 # every symbol include/airband_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "abg_last_error", "abg_version", "abg_create", "abg_destroy", "abg_wave_batch", "abg_hop", "abg_push",
-    "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_get_stats", "abg_set_bin",
+    "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_fetch_batches", "abg_get_stats", "abg_set_bin",
     "abg_resident_load", "abg_run_resident", "abg_set_stream", "abg_launch_count", "abg_mixers_configure",
     "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times",
 ]
@@ -72,6 +72,7 @@ def load():
     L.abg_join.restype, L.abg_join.argtypes = i, [vp]
     L.abg_batches_ready.restype, L.abg_batches_ready.argtypes = i, [vp, i]
     L.abg_fetch_batch.restype, L.abg_fetch_batch.argtypes = i, [vp, i, vp, vp, vp]
+    L.abg_fetch_batches.restype, L.abg_fetch_batches.argtypes = i, [vp, i, i, vp, vp, vp]
     L.abg_get_stats.restype, L.abg_get_stats.argtypes = i, [vp, i, i, C.POINTER(CSquelchStats)]
     L.abg_set_bin.restype, L.abg_set_bin.argtypes = i, [vp, i, i, i]
     L.abg_resident_load.restype, L.abg_resident_load.argtypes = i, [vp, i, vp, C.c_size_t]
@@ -157,6 +158,10 @@ class Engine:
 
     def fetch_into(self, dev: int, wo: np.ndarray, ax: np.ndarray) -> bool:
         return bool(self._chk(self.L.abg_fetch_batch(self.h, dev, _ptr(wo), None, _ptr(ax))))
+
+    def fetch_many_into(self, dev: int, max_batches: int, wo: np.ndarray, ax: np.ndarray) -> int:
+        """Pop up to max_batches batches of a device into wo[n, C, B] / ax[n, C]; returns how many."""
+        return self._chk(self.L.abg_fetch_batches(self.h, dev, max_batches, _ptr(wo), None, _ptr(ax)))
 
     def fetch_all(self, dev: int):
         wos, iqs, axs = [], [], []

@@ -242,3 +242,40 @@ def test_host_adapter_thread_function_matches_oracle():
         assert gate(gw, ow) <= TOL
         assert info["overflows"] == 0 and info["overruns"] == 0
         assert info["active"] == [int(np.sum(oa[:, c] != ord(' '))) for c in range(ow.shape[0])]
+
+
+def test_bulk_fetch_equals_single_fetches():
+    cfg, raws = CASES["am_u8"](n_batches=4)
+    e1 = lib.Engine(cfg, max_batches_per_run=4)
+    e2 = lib.Engine(cfg, max_batches_per_run=4)
+    for e in (e1, e2):
+        e.push(0, raws[0])
+        assert e.run(-1) == 4
+    singles = [e1.fetch(0) for _ in range(4)]
+    C = len(cfg.devices[0].channels)
+    wo = np.empty((4, C, cfg.wave_batch), np.float32)
+    ax = np.empty((4, C), np.uint8)
+    assert e2.fetch_many_into(0, 8, wo, ax) == 4 and e2.fetch(0) is None
+    for b in range(4):
+        assert np.array_equal(wo[b], singles[b][0]) and np.array_equal(ax[b], singles[b][2])
+
+
+def test_error_codes():
+    """Error behaviour of the C ABI mirrors the reference's engine branch: message + negative code, no exceptions cross."""
+    cfg = wl.cfg1()
+    bad = cm.Config(fft_size=300, wave_rate=8000, devices=cfg.devices)
+    with pytest.raises(lib.AbgError) as ei:
+        lib.Engine(bad)
+    assert ei.value.code == -2 and "not supported" in str(ei.value)
+    e = lib.Engine(cfg, max_batches_per_run=1, input_capacity_batches=1)
+    with pytest.raises(lib.AbgError) as ei:
+        e.push(5, np.zeros(16, np.uint8))
+    assert ei.value.code == -5
+    with pytest.raises(lib.AbgError) as ei:
+        e.push(0, np.zeros(3, np.uint8))  # not a whole number of complex samples
+    assert ei.value.code == -2
+    big = np.zeros(2 * 320 * 1000 * 4, np.uint8)  # four batches into a one-batch buffer
+    with pytest.raises(lib.AbgError) as ei:
+        e.push(0, big)
+    assert ei.value.code == -6
+    assert e.fetch(0) is None and e.run(-1) == 0
