@@ -83,7 +83,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -189,8 +189,8 @@ def cpu_run(cfg, desc, steps: int, warmup: int, budget_s: float = 20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--batches-per-step", type=int, default=4)
@@ -248,12 +248,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-timed, inputs resident in HBM ----
-    for _ in range(max(args.warmup, 1)):
-        eng.run_resident(nb)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        eng.run_resident(nb)
+    barrier()
+    if rank == 0:
+        sampler.rows.clear()  # keep only samples taken during the timed region
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_ms, k2_ms = [], []
