@@ -168,6 +168,9 @@ ABG_API uint64_t abg_launch_count(const abg_engine* e);
  * ms4[0] = K1 (convert+window+FFT+bins, all groups), ms4[1] = K2 (demodulation), ms4[2] = mixers + result copies + tail
  * copy, ms4[3] = whole run.  Waits for that run to finish. */
 ABG_API int abg_last_run_times(abg_engine* e, float* ms4);
+/* Measurement aid: 5 timestamps (K1 start, K1 end, K2 start, K2 end, end of run; ms since the oldest run's K1 start) for
+   each of the last n_runs (1..8) runs into ms[5*n_runs]; shows how consecutive runs overlap on the device. */
+ABG_API int abg_debug_timeline(abg_engine* e, int n_runs, float* ms);
 
 /* Mixer path (reference src/mixer.cpp:82-83,114-140,189-214): mixer m's output for a batch is, per sample,
  * sum over its inputs (in input order) of waveout * (ampfactor * ampl) [left] and * (ampfactor * ampr) [right], taken

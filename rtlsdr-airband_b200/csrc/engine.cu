@@ -213,12 +213,13 @@ struct abg_engine {
     cudaEvent_t ev_ingest = nullptr; // last ingest operation
     bool ingest_dirty = false;
     cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr};
-    cudaEvent_t tev_b[3] = {nullptr, nullptr, nullptr};  // stream B: before K2 / after K2 / end of run
     uint64_t run_index = 0;
     bool any_afc = false;
     int k2_lpw = 32;
     uint64_t launches = 0;
-    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // run start / after K1 / after K2 / run end
+    // timing events of the last TL_RUNS runs: [0] K1 start, [1] K1 end (stream A); [2] K2 start, [3] K2 end, [4] end of run (stream B)
+    static constexpr int TL_RUNS = 8;
+    cudaEvent_t tl[TL_RUNS][5] = {};
     bool tev_valid = false;
     std::vector<int32_t> h_bins;
     // mixers (reference src/mixer.cpp)
@@ -279,10 +280,9 @@ void engine_free(abg_engine* e) {
         if (s.mixflag) cudaFreeHost(s.mixflag);
         if (s.done) cudaEventDestroy(s.done);
     }
-    for (auto& ev : e->tev)
-        if (ev) cudaEventDestroy(ev);
-    for (auto& ev : e->tev_b)
-        if (ev) cudaEventDestroy(ev);
+    for (auto& row : e->tl)
+        for (auto& ev : row)
+            if (ev) cudaEventDestroy(ev);
     for (int k = 0; k < 2; k++) {
         if (e->ev_k1[k]) cudaEventDestroy(e->ev_k1[k]);
         if (e->ev_k2[k]) cudaEventDestroy(e->ev_k2[k]);
@@ -517,7 +517,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         CU(cudaEventCreateWithFlags(&e->ev_k1[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->ev_k2[k], cudaEventDisableTiming));
     }
-    for (auto& ev : e->tev_b) CU(cudaEventCreate(&ev));
+    for (auto& row : e->tl)
+        for (auto& ev : row) CU(cudaEventCreate(&ev));
     CU(cudaStreamCreateWithFlags(&e->stream_c, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&e->ev_ingest, cudaEventDisableTiming));
     for (auto& d : e->dev)
@@ -614,7 +615,6 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         CU(cudaMallocHost((void**)&s.axc, (size_t)e->nbmax * Gp));
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
-    for (auto& ev : e->tev) CU(cudaEventCreate(&ev));
     CU(cudaStreamSynchronize(e->stream));
     return ABG_OK;
 }
@@ -648,7 +648,8 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         CU(cudaStreamWaitEvent(sa, e->ev_ingest, 0));
         e->ingest_dirty = false;
     }
-    CU(cudaEventRecord(e->tev[0], sa));
+    cudaEvent_t* tl = e->tl[ri % abg_engine::TL_RUNS];
+    CU(cudaEventRecord(tl[0], sa));
     // ---- K1 per group (stream A) ----
     const int stg = (int)(ri & 3);
     for (auto& g : e->groups) {
@@ -685,7 +686,7 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         if (er1 != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er1));
         e->launches += g.pruned ? (uint64_t)((g.max_channels + 31) / 32) : 1;
     }
-    CU(cudaEventRecord(e->tev[1], sa));
+    CU(cudaEventRecord(tl[1], sa));
     CU(cudaEventRecord(e->ev_k1[cur], sa));
     // ---- K2 (stream B, after this run's K1; overlaps the next run's K1) ----
     CU(cudaStreamWaitEvent(sb, e->ev_k1[cur], 0));
@@ -697,12 +698,12 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     }
     CU(cudaMemcpyAsync(e->d_k2, e->h_k2[stg], sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, sb));
     CU(cudaEventRecord(e->k2_stage_done[stg], sb));
-    CU(cudaEventRecord(e->tev_b[0], sb));
+    CU(cudaEventRecord(tl[2], sb));
     K2Launch L2 = e->k2_launch(cur);
     cudaError_t er = abg_launch_k2(L2, sb);
     if (er != cudaSuccess) return fail(ABG_ECUDA, "K2 launch failed: %s", cudaGetErrorString(er));
     e->launches++;
-    CU(cudaEventRecord(e->tev_b[1], sb));
+    CU(cudaEventRecord(tl[3], sb));
     // ---- mixers: sums over the just-finished batches, before the tail copy (output.cpp:533-535 -> mixer.cpp) ----
     if (e->n_mixers > 0) {
         MixLaunch M{};
@@ -742,7 +743,7 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
                 s.mix_pending += e->n_mixers;
             }
     }
-    CU(cudaEventRecord(e->tev_b[2], sb));
+    CU(cudaEventRecord(tl[4], sb));
     CU(cudaEventRecord(e->ev_k2[cur], sb));
     e->tev_valid = true;
     e->run_index++;
@@ -1011,11 +1012,28 @@ uint64_t abg_launch_count(const abg_engine* e) { return e->launches; }
 int abg_last_run_times(abg_engine* e, float* ms4) {
     if (!e->tev_valid) return fail(ABG_EINVAL, "abg_last_run_times: no run yet");
     cudaSetDevice(e->cuda_dev);
-    CU(cudaEventSynchronize(e->tev_b[2]));
-    CU(cudaEventElapsedTime(&ms4[0], e->tev[0], e->tev[1]));      // K1 on stream A
-    CU(cudaEventElapsedTime(&ms4[1], e->tev_b[0], e->tev_b[1]));  // K2 on stream B
-    CU(cudaEventElapsedTime(&ms4[2], e->tev_b[1], e->tev_b[2]));  // mixers + result copies + tail copy
-    CU(cudaEventElapsedTime(&ms4[3], e->tev[0], e->tev_b[2]));    // first K1 launch to end of run
+    cudaEvent_t* tl = e->tl[(e->run_index - 1) % abg_engine::TL_RUNS];
+    CU(cudaEventSynchronize(tl[4]));
+    CU(cudaEventElapsedTime(&ms4[0], tl[0], tl[1]));  // K1 on stream A
+    CU(cudaEventElapsedTime(&ms4[1], tl[2], tl[3]));  // K2 on stream B
+    CU(cudaEventElapsedTime(&ms4[2], tl[3], tl[4]));  // mixers + result export + tail copy
+    CU(cudaEventElapsedTime(&ms4[3], tl[0], tl[4]));  // first K1 launch to end of run
+    return ABG_OK;
+}
+
+// Timeline of the last n_runs (<= 8) runs: 5 timestamps per run (K1 start, K1 end, K2 start, K2 end, end of run) in ms
+// relative to the oldest run's K1 start.  Measurement aid: shows how runs overlap inside the stream pipeline.
+int abg_debug_timeline(abg_engine* e, int n_runs, float* ms) {
+    if (!ms || n_runs < 1 || n_runs > abg_engine::TL_RUNS || (uint64_t)n_runs > e->run_index)
+        return fail(ABG_EINVAL, "abg_debug_timeline: bad arguments");
+    cudaSetDevice(e->cuda_dev);
+    cudaEvent_t* last = e->tl[(e->run_index - 1) % abg_engine::TL_RUNS];
+    CU(cudaEventSynchronize(last[4]));
+    cudaEvent_t origin = e->tl[(e->run_index - n_runs) % abg_engine::TL_RUNS][0];
+    for (int r = 0; r < n_runs; r++) {
+        cudaEvent_t* tl = e->tl[(e->run_index - n_runs + r) % abg_engine::TL_RUNS];
+        for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ms[r * 5 + k], origin, tl[k]));
+    }
     return ABG_OK;
 }
 

@@ -17,6 +17,7 @@
 // Frames of a tile are staged once by a TMA bulk copy exactly as in k1_fft.cu (frames overlap by N-hop samples).
 // Devices with AFC need the whole spectrum of batch-final frames (reference src/rtl_airband.cpp:180-251) and keep
 // using the full-spectrum kernel.
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -301,7 +302,14 @@ int pr_cm(int max_channels) {  // channels per pass: multiple of 4, at most PR_M
 
 template <int LOGN, int SFMT, int R1, int GE>
 cudaError_t pr_launch_one2(const K1Launch& L, const PrArgs& args, cudaStream_t s) {
-    const size_t smem = pr_fixed_smem(1 << LOGN, R1, args.nchmax) + (size_t)L.tile_bytes_cap;
+    size_t smem = pr_fixed_smem(1 << LOGN, R1, args.nchmax) + (size_t)L.tile_bytes_cap;
+    // experiment knob: cap the resident CTAs per SM by padding the shared-memory request (228 KB per SM, 1 KB reserved per CTA)
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        const char* e = getenv("ABG_K1_MAX_CTAS_PER_SM");
+        max_ctas = e ? atoi(e) : 0;
+    }
+    if (max_ctas > 0) smem = std::max(smem, (size_t)(228 * 1024 / (max_ctas + 1) + 1024));
     auto kern = k1_pruned_kernel<LOGN, SFMT, R1, GE>;
     static size_t configured = 0;
     if (smem > configured) {

@@ -15,14 +15,14 @@ from .config import CConfig, CSquelchStats, Config
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.abspath(os.path.join(_HERE, "..", ".."))
-LIB_PATH = os.path.join(LIB_DIR, "libairband_b200.so")
+LIB_PATH = os.environ.get("ABG_LIB_PATH") or os.path.join(LIB_DIR, "libairband_b200.so")  # override: A/B-testing builds
 
 # every symbol include/airband_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "abg_last_error", "abg_version", "abg_create", "abg_destroy", "abg_wave_batch", "abg_hop", "abg_push",
     "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_fetch_batches", "abg_get_stats", "abg_set_bin",
     "abg_resident_load", "abg_run_resident", "abg_set_stream", "abg_launch_count", "abg_mixers_configure",
-    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times",
+    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     L.abg_mixer_device_buffers.restype, L.abg_mixer_device_buffers.argtypes = i, [vp, C.POINTER(vp), C.POINTER(vp)]
     L.abg_debug_frame.restype, L.abg_debug_frame.argtypes = i, [vp, i, vp, vp]
     L.abg_last_run_times.restype, L.abg_last_run_times.argtypes = i, [vp, C.POINTER(C.c_float)]
+    L.abg_debug_timeline.restype, L.abg_debug_timeline.argtypes = i, [vp, i, C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -204,6 +205,12 @@ class Engine:
         a = (C.c_float * 4)()
         self._chk(self.L.abg_last_run_times(self.h, a))
         return tuple(float(x) for x in a)
+
+    def timeline(self, n_runs: int = 8) -> np.ndarray:
+        """[n_runs, 5] ms: K1 start, K1 end, K2 start, K2 end, end of run, relative to the oldest run's K1 start."""
+        a = (C.c_float * (5 * n_runs))()
+        self._chk(self.L.abg_debug_timeline(self.h, n_runs, a))
+        return np.array(a, dtype=np.float32).reshape(n_runs, 5)
 
     def launch_count(self) -> int:
         return int(self.L.abg_launch_count(self.h))
