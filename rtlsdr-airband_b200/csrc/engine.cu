@@ -29,6 +29,33 @@
 
 namespace {
 
+// Small host->device parameter uploads go through a KERNEL (payload passed by value), not cudaMemcpyAsync: a copy would
+// queue on the host->device copy engine behind whatever bulk ingest copies (abg_push of the NEXT run) are already
+// enqueued, and the run that needs these few hundred bytes would wait for megabytes of unrelated input (measured: ~1 ms
+// per step on the pipelined host path).  A launch is ordered only by its own stream.
+struct UploadBlob {
+    uint4 q[240];  // 3840 bytes: stays below the 4 KB kernel-parameter limit together with the other arguments
+};
+__global__ void upload_kernel(const UploadBlob b, uint4* dst, int n16) {
+    const int i = threadIdx.x;
+    if (i < n16) dst[i] = b.q[i];
+}
+// dst: 16-byte aligned device buffer with room for nbytes rounded up to 16; returns the number of launches (or -1)
+int upload_small(void* dst, const void* src, size_t nbytes, cudaStream_t s) {
+    int launches = 0;
+    for (size_t off = 0; off < nbytes; off += sizeof(UploadBlob)) {
+        const size_t chunk = std::min(sizeof(UploadBlob), nbytes - off);
+        UploadBlob b;
+        memcpy(b.q, static_cast<const char*>(src) + off, chunk);
+        if (chunk % 16) memset(reinterpret_cast<char*>(b.q) + chunk, 0, 16 - chunk % 16);
+        const int n16 = (int)((chunk + 15) / 16);
+        upload_kernel<<<1, 256, 0, s>>>(b, reinterpret_cast<uint4*>(static_cast<char*>(dst) + off), n16);
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        ++launches;
+    }
+    return launches;
+}
+
 thread_local std::string g_err;
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -168,10 +195,7 @@ struct Group {
     bool pruned = false;                               // which kernel this group runs
     DevBuf<float> wsc;
     K1Dev* d_k1 = nullptr;  // device array [devs.size()]
-    // pinned staging ring (a pageable source would make cudaMemcpyAsync synchronise the stream first and serialise the
-    // K1/K2 pipeline); a slot is reused only after the copy that read it has completed (stage_done)
-    K1Dev* h_k1[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t stage_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<K1Dev> h_k1;  // host copy, uploaded by value with every run (upload_small)
 };
 
 struct Slot {
@@ -202,8 +226,7 @@ struct abg_engine {
     DevBuf<float2> iqin[2], iqout, tw1, tw2, twn;                                           // fills one while K2 of run i reads the other
     DevBuf<unsigned char> axc;
     K2Dev* d_k2 = nullptr;
-    K2Dev* h_k2[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring (see Group::h_k1)
-    cudaEvent_t k2_stage_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<K2Dev> h_k2;  // host copy, uploaded by value with every run (upload_small)
     std::vector<Slot> slots;
     int next_slot = 0;
     cudaStream_t stream = nullptr;   // stream A: ingest copies + K1
@@ -259,19 +282,11 @@ void engine_free(abg_engine* e) {
     for (auto& g : e->groups) {
         g.wsc.free();
         if (g.d_k1) cudaFree(g.d_k1);
-        for (int k = 0; k < 4; k++) {
-            if (g.h_k1[k]) cudaFreeHost(g.h_k1[k]);
-            if (g.stage_done[k]) cudaEventDestroy(g.stage_done[k]);
-        }
     }
     e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win[0].free(); e->win[1].free(); e->wout.free(); e->sqbuf.free();
     e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin[0].free(); e->iqin[1].free(); e->iqout.free();
     e->tw1.free(); e->tw2.free(); e->twn.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
     if (e->d_k2) cudaFree(e->d_k2);
-    for (int k = 0; k < 4; k++) {
-        if (e->h_k2[k]) cudaFreeHost(e->h_k2[k]);
-        if (e->k2_stage_done[k]) cudaEventDestroy(e->k2_stage_done[k]);
-    }
     for (auto& s : e->slots) {
         if (s.wout) cudaFreeHost(s.wout);
         if (s.iqout) cudaFreeHost(s.iqout);
@@ -552,11 +567,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         for (int i = 0; i < N; i++) wsc[i] = window[i] * scale;
         CU(g.wsc.alloc(N));
         CU(cudaMemcpy(g.wsc.p, wsc.data(), N * sizeof(float), cudaMemcpyHostToDevice));
-        CU(cudaMalloc((void**)&g.d_k1, sizeof(K1Dev) * g.devs.size()));
-        for (int k = 0; k < 4; k++) {
-            CU(cudaMallocHost((void**)&g.h_k1[k], sizeof(K1Dev) * g.devs.size()));
-            CU(cudaEventCreateWithFlags(&g.stage_done[k], cudaEventDisableTiming));
-        }
+        CU(cudaMalloc((void**)&g.d_k1, sizeof(K1Dev) * g.devs.size() + 16));
+        g.h_k1.assign(g.devs.size(), K1Dev{});
     }
     for (auto& d : e->dev) {
         // room for in_cap_batches batches + the AGC_EXTRA priming frames + one window, + slack for 16-byte TMA rounding
@@ -603,11 +615,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         CU(cudaMemcpy(e->win[1].p, hw.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(e->wout.p, ho.data(), sizeof(float) * PG, cudaMemcpyHostToDevice));
     }
-    CU(cudaMalloc((void**)&e->d_k2, sizeof(K2Dev) * e->dev.size()));
-    for (int k = 0; k < 4; k++) {
-        CU(cudaMallocHost((void**)&e->h_k2[k], sizeof(K2Dev) * e->dev.size()));
-        CU(cudaEventCreateWithFlags(&e->k2_stage_done[k], cudaEventDisableTiming));
-    }
+    CU(cudaMalloc((void**)&e->d_k2, sizeof(K2Dev) * e->dev.size() + 16));
+    e->h_k2.assign(e->dev.size(), K2Dev{});
     e->slots.resize(3);
     for (auto& s : e->slots) {
         CU(cudaMallocHost((void**)&s.wout, sizeof(float) * (size_t)std::max(G, 1) * e->nbmax * B));
@@ -651,14 +660,12 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     cudaEvent_t* tl = e->tl[ri % abg_engine::TL_RUNS];
     CU(cudaEventRecord(tl[0], sa));
     // ---- K1 per group (stream A) ----
-    const int stg = (int)(ri & 3);
     for (auto& g : e->groups) {
         int max_frames = 0;
-        if (ri >= 4) CU(cudaEventSynchronize(g.stage_done[stg]));
         for (size_t k = 0; k < g.devs.size(); k++) {
             const int di = g.devs[k];
             Device& d = e->dev[di];
-            K1Dev& a = g.h_k1[stg][k];
+            K1Dev& a = g.h_k1[k];
             const bool primed = resident ? d.res_primed : d.primed;
             a.raw = resident ? d.res : d.raw[d.cur];
             a.n_frames = nb[di] > 0 ? nb[di] * B + (primed ? 0 : ABG_AGC_EXTRA) : 0;
@@ -674,8 +681,11 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
             max_frames = std::max(max_frames, a.n_frames);
         }
         if (max_frames == 0) continue;
-        CU(cudaMemcpyAsync(g.d_k1, g.h_k1[stg], sizeof(K1Dev) * g.devs.size(), cudaMemcpyHostToDevice, sa));
-        CU(cudaEventRecord(g.stage_done[stg], sa));
+        {
+            const int nl = upload_small(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), sa);
+            if (nl < 0) return fail(ABG_ECUDA, "K1 parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            e->launches += (uint64_t)nl;
+        }
         K1Launch L{};
         L.fft_size = N; L.n_devices = (int)g.devs.size(); L.max_frames = max_frames;
         L.frames_per_tile = g.pruned ? g.p_frames_per_tile : g.frames_per_tile;
@@ -690,14 +700,16 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     CU(cudaEventRecord(e->ev_k1[cur], sa));
     // ---- K2 (stream B, after this run's K1; overlaps the next run's K1) ----
     CU(cudaStreamWaitEvent(sb, e->ev_k1[cur], 0));
-    if (ri >= 4) CU(cudaEventSynchronize(e->k2_stage_done[stg]));
     for (size_t i = 0; i < e->dev.size(); i++) {
-        e->h_k2[stg][i].n_batches = nb[i];
-        e->h_k2[stg][i].fft_size = N;
-        e->h_k2[stg][i].spec = e->dev[i].has_afc ? e->dev[i].spec : nullptr;
+        e->h_k2[i].n_batches = nb[i];
+        e->h_k2[i].fft_size = N;
+        e->h_k2[i].spec = e->dev[i].has_afc ? e->dev[i].spec : nullptr;
     }
-    CU(cudaMemcpyAsync(e->d_k2, e->h_k2[stg], sizeof(K2Dev) * e->dev.size(), cudaMemcpyHostToDevice, sb));
-    CU(cudaEventRecord(e->k2_stage_done[stg], sb));
+    {
+        const int nl = upload_small(e->d_k2, e->h_k2.data(), sizeof(K2Dev) * e->dev.size(), sb);
+        if (nl < 0) return fail(ABG_ECUDA, "K2 parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        e->launches += (uint64_t)nl;
+    }
     CU(cudaEventRecord(tl[2], sb));
     K2Launch L2 = e->k2_launch(cur);
     cudaError_t er = abg_launch_k2(L2, sb);
