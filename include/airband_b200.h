@@ -167,6 +167,18 @@ ABG_API uint64_t abg_launch_count(const abg_engine* e);
 /* Device time of the most recent run, from CUDA events recorded on the engine's stream around its kernels:
  * ms4[0] = K1 (convert+window+FFT+bins, all groups), ms4[1] = K2 (demodulation), ms4[2] = mixers + result copies + tail
  * copy, ms4[3] = whole run.  Waits for that run to finish. */
+/* Scan mode.  Reference: an R_SCAN device has one channel with freqlist[freq_count] (src/rtl_airband.h:250-252); every
+   freq_t owns its Squelch, NotchFilter, LowpassFilter, agcavgfast, ampfactor, modulation and active_counter
+   (src/rtl_airband.h:223-233).  controller_thread switches channels[0].freq_idx and retunes the input
+   (src/rtl_airband.cpp:101-139); demodulate() picks fparms = freqlist + freq_idx at the start of every batch (:498).
+   abg_scan_configure installs the list for a channel: freqs[i] supplies the freq_t part of entry i (modulation,
+   ampfactor, squelch_*, lowpass_hz, notch_*, ctcss_hz; the channel_t part - bin, dm_dphi, alpha, afc, needs_raw_iq,
+   has_iq_outputs - stays what abg_create was given).  Every entry starts from a fresh freq_t; entry 0 becomes current.
+   abg_scan_select makes entry freq_idx current for all batches demodulated by later abg_run calls; the state of the
+   entry it replaces is kept on the device and resumes when that entry is selected again. */
+ABG_API int abg_scan_configure(abg_engine* e, int dev, int chan, int n_freqs, const abg_channel_cfg* freqs);
+ABG_API int abg_scan_select(abg_engine* e, int dev, int chan, int freq_idx);
+
 ABG_API int abg_last_run_times(abg_engine* e, float* ms4);
 /* Measurement aid: 5 timestamps (K1 start, K1 end, K2 start, K2 end, end of run; ms since the oldest run's K1 start) for
    each of the last n_runs (1..8) runs into ms[5*n_runs]; shows how consecutive runs overlap on the device. */

@@ -84,6 +84,10 @@ int abo_batches_ready(void* h, int dev);
 int abo_fetch_batch(void* h, int dev, float* waveout, float* iq_out, char* axc);
 int abo_get_stats(void* h, int dev, int chan, abo_squelch_stats* out);
 int abo_set_bin(void* h, int dev, int chan, int bin);
+/* scan mode (rtl_airband.h:250-252, rtl_airband.cpp:101-139,498): install a frequency list for a channel (entry 0
+ * current, all entries fresh); select the entry the next batch uses */
+int abo_scan_configure(void* h, int dev, int chan, int n_freqs, const abo_channel_cfg* freqs);
+int abo_scan_select(void* h, int dev, int chan, int freq_idx);
 /* the stage boundaries, for tests: window[N]; one frame converted+windowed (2N floats) and its spectrum (2N) */
 int abo_get_window(void* h, float* window);
 int abo_debug_frame(void* h, int dev, const void* iq_frame, float* fftin, float* fftout);

@@ -101,6 +101,16 @@ float polar_disc_fast(float ar, float aj, float br, float bj) {
 }
 float fm_quadri_demod(float ar, float aj, float br, float bj) { return (float)((br * aj - ar * bj) / (ar * ar + aj * aj + 1.0f) * M_1_PI); }
 
+// freq_t, rtl_airband.h:223-233
+struct Freq {
+    float agcavgfast = 0.5f, ampfactor = 1.0f;
+    int modulation = ABO_MOD_AM;
+    uint64_t active_counter = 0;
+    Squelch squelch;
+    NotchFilter notch_filter;
+    LowpassFilter lowpass_filter;
+};
+
 struct Channel {
     // channel_t, rtl_airband.h:234-263 (only what the hot path touches)
     std::vector<float> wavein, waveout, iq_in, iq_out;
@@ -109,13 +119,9 @@ struct Channel {
     int axcindicate = NO_SIGNAL;
     int afc = 0;
     int needs_raw_iq = 0, has_iq_outputs = 0;
-    // freq_t, rtl_airband.h:223-233
-    float agcavgfast = 0.5f, ampfactor = 1.0f;
-    int modulation = ABO_MOD_AM;
-    uint64_t active_counter = 0;
-    Squelch squelch;
-    NotchFilter notch_filter;
-    LowpassFilter lowpass_filter;
+    // scan mode: freqlist / freq_idx, rtl_airband.h:250-252 (one entry unless abo_scan_configure() installs a list)
+    std::vector<std::unique_ptr<Freq>> freqlist;
+    int freq_idx = 0;
 };
 
 struct Batch {
@@ -226,70 +232,85 @@ void convert_frame(const Oracle& o, const Device& d, const unsigned char* p, flo
     }
 }
 
+// one freq_t as parse_channels() sets it up (config.cpp:437-619: level first, SNR (if given) afterwards)
+std::unique_ptr<Freq> make_freq(const abo_channel_cfg& cc, int wave_rate) {
+    std::unique_ptr<Freq> fp(new Freq());
+    Freq& f = *fp;
+    f.ampfactor = cc.ampfactor;
+    f.modulation = cc.modulation;
+    if (cc.squelch_level > 0) f.squelch.set_squelch_level_threshold(cc.squelch_level);
+    if (cc.squelch_snr_db >= 0) f.squelch.set_squelch_snr_threshold(cc.squelch_snr_db);
+    if (cc.notch_hz > 0) f.notch_filter = NotchFilter(cc.notch_hz, wave_rate, cc.notch_q);
+    if (cc.ctcss_hz > 0) f.squelch.set_ctcss_freq(cc.ctcss_hz, wave_rate);
+    if (cc.lowpass_hz > 0) f.lowpass_filter = LowpassFilter(cc.lowpass_hz, wave_rate);
+    return fp;
+}
+
 // the per-sample channel loop of one batch, rtl_airband.cpp:495-648
 void demod_batch(Oracle& o, Device& d, const float* last_fftout) {
     const int B = o.wave_batch;
     for (size_t i = 0; i < d.ch.size(); i++) {
         Channel& c = *d.ch[i];
+        Freq& f = *c.freqlist[c.freq_idx];  // fparms = channel->freqlist + channel->freq_idx, rtl_airband.cpp:498
         Afc afc(c, o.fft_size);
         c.axcindicate = NO_SIGNAL;
         for (int j = AGC_EXTRA; j < B + AGC_EXTRA; j++) {
             float& real = c.iq_in[2 * (j - AGC_EXTRA)];
             float& imag = c.iq_in[2 * (j - AGC_EXTRA) + 1];
 
-            c.squelch.process_raw_sample(c.wavein[j]);
+            f.squelch.process_raw_sample(c.wavein[j]);
 
-            if (c.squelch.should_filter_sample() && c.needs_raw_iq) {
+            if (f.squelch.should_filter_sample() && c.needs_raw_iq) {
                 float swf, cwf, re_tmp, im_tmp;
                 g_lut.get(c.dm_phi, &swf, &cwf);
                 multiply(real, imag, cwf, -swf, &re_tmp, &im_tmp);
                 c.dm_phi += c.dm_dphi;
                 c.dm_phi &= 0xffffff;
-                c.lowpass_filter.apply(re_tmp, im_tmp);
+                f.lowpass_filter.apply(re_tmp, im_tmp);
                 real = re_tmp;
                 imag = im_tmp;
                 c.wavein[j] = sqrt(real * real + imag * imag);
-                if (c.lowpass_filter.enabled()) c.squelch.process_filtered_sample(c.wavein[j]);
+                if (f.lowpass_filter.enabled()) f.squelch.process_filtered_sample(c.wavein[j]);
             }
 
-            if (c.modulation == ABO_MOD_AM) {
-                if (c.squelch.first_open_sample()) {
+            if (f.modulation == ABO_MOD_AM) {
+                if (f.squelch.first_open_sample()) {
                     for (int k = j - AGC_EXTRA; k < j; k++) {
-                        if (c.wavein[k] >= c.squelch.squelch_level()) c.agcavgfast = c.agcavgfast * 0.9f + c.wavein[k] * 0.1f;
+                        if (c.wavein[k] >= f.squelch.squelch_level()) f.agcavgfast = f.agcavgfast * 0.9f + c.wavein[k] * 0.1f;
                     }
-                } else if (c.squelch.last_open_sample()) {
+                } else if (f.squelch.last_open_sample()) {
                     for (int k = j - AGC_EXTRA + 1; k < j; k++) c.waveout[k] = c.waveout[k - 1] * 0.94f;
                 }
             }
 
             float& waveout = c.waveout[j];
 
-            if (c.squelch.should_process_audio()) {
-                if (c.modulation == ABO_MOD_AM) {
-                    if (c.wavein[j] > c.squelch.squelch_level()) c.agcavgfast = c.agcavgfast * 0.995f + c.wavein[j] * 0.005f;
-                    waveout = (c.wavein[j - AGC_EXTRA] - c.agcavgfast) / (c.agcavgfast * 1.5f);
+            if (f.squelch.should_process_audio()) {
+                if (f.modulation == ABO_MOD_AM) {
+                    if (c.wavein[j] > f.squelch.squelch_level()) f.agcavgfast = f.agcavgfast * 0.995f + c.wavein[j] * 0.005f;
+                    waveout = (c.wavein[j - AGC_EXTRA] - f.agcavgfast) / (f.agcavgfast * 1.5f);
                     if (std::abs(waveout) > 0.8f) {
                         waveout *= 0.85f;
-                        c.agcavgfast *= 1.15f;
+                        f.agcavgfast *= 1.15f;
                     }
-                } else if (c.modulation == ABO_MOD_NFM) {
+                } else if (f.modulation == ABO_MOD_NFM) {
                     if (o.fm_demod == ABO_FM_FAST_ATAN2)
                         waveout = polar_disc_fast(real, imag, c.pr, c.pj);
                     else if (o.fm_demod == ABO_FM_QUADRI_DEMOD)
                         waveout = fm_quadri_demod(real, imag, c.pr, c.pj);
                     c.pr = real;
                     c.pj = imag;
-                    c.agcavgfast = c.agcavgfast * 0.995f + waveout * 0.005f;
-                    waveout -= c.agcavgfast;
+                    f.agcavgfast = f.agcavgfast * 0.995f + waveout * 0.005f;
+                    waveout -= f.agcavgfast;
                     waveout = waveout * (1.0f - c.alpha) + c.prev_waveout * c.alpha;
                     c.prev_waveout = waveout;
                 }
-                c.squelch.process_audio_sample(waveout);
+                f.squelch.process_audio_sample(waveout);
             }
 
-            if (c.squelch.is_open()) {
-                c.notch_filter.apply(waveout);
-                waveout *= c.ampfactor;
+            if (f.squelch.is_open()) {
+                f.notch_filter.apply(waveout);
+                waveout *= f.ampfactor;
                 if (std::isnan(waveout)) {
                     waveout = 0.0;
                 } else if (waveout > 1.0) {
@@ -315,7 +336,7 @@ void demod_batch(Oracle& o, Device& d, const float* last_fftout) {
 
         afc.finalize(d, (int)i, last_fftout);
 
-        if (c.axcindicate != NO_SIGNAL) c.active_counter++;
+        if (c.axcindicate != NO_SIGNAL) f.active_counter++;
     }
 
     // output thread, run synchronously: consume waveout[0..B) / iq_out[0..2B), then the tail copy (output.cpp:917-922)
@@ -438,14 +459,7 @@ void* abo_create(const abo_config* cfg) {
             c.afc = cc.afc;
             c.needs_raw_iq = cc.needs_raw_iq;
             c.has_iq_outputs = cc.has_iq_outputs;
-            c.ampfactor = cc.ampfactor;
-            c.modulation = cc.modulation;
-            // config.cpp:437-515: level first, SNR (if given) afterwards
-            if (cc.squelch_level > 0) c.squelch.set_squelch_level_threshold(cc.squelch_level);
-            if (cc.squelch_snr_db >= 0) c.squelch.set_squelch_snr_threshold(cc.squelch_snr_db);
-            if (cc.notch_hz > 0) c.notch_filter = NotchFilter(cc.notch_hz, o->wave_rate, cc.notch_q);
-            if (cc.ctcss_hz > 0) c.squelch.set_ctcss_freq(cc.ctcss_hz, o->wave_rate);
-            if (cc.lowpass_hz > 0) c.lowpass_filter = LowpassFilter(cc.lowpass_hz, o->wave_rate);
+            c.freqlist.push_back(make_freq(cc, o->wave_rate));
             d.bins.push_back((size_t)cc.bin);
             d.base_bins.push_back((size_t)cc.bin);
             d.ch.push_back(std::move(cp));
@@ -513,17 +527,43 @@ int abo_get_stats(void* h, int dev, int chan, abo_squelch_stats* out) {
     Device& d = o->D(dev);
     if (chan < 0 || chan >= (int)d.ch.size()) return -1;
     Channel& c = *d.ch[chan];
-    out->noise_level = c.squelch.noise_level();
-    out->signal_level = c.squelch.signal_level();
-    out->squelch_level = c.squelch.squelch_level();
-    out->open_count = c.squelch.open_count();
-    out->flappy_count = c.squelch.flappy_count();
-    out->ctcss_count = c.squelch.ctcss_count();
-    out->no_ctcss_count = c.squelch.no_ctcss_count();
-    out->agcavgfast = c.agcavgfast;
+    Freq& f = *c.freqlist[c.freq_idx];
+    out->noise_level = f.squelch.noise_level();
+    out->signal_level = f.squelch.signal_level();
+    out->squelch_level = f.squelch.squelch_level();
+    out->open_count = f.squelch.open_count();
+    out->flappy_count = f.squelch.flappy_count();
+    out->ctcss_count = f.squelch.ctcss_count();
+    out->no_ctcss_count = f.squelch.no_ctcss_count();
+    out->agcavgfast = f.agcavgfast;
     out->dm_phi = c.dm_phi;
     out->bin = (int32_t)d.bins[chan];
-    out->active_counter = c.active_counter;
+    out->active_counter = f.active_counter;
+    return 0;
+}
+
+// scan mode: install a frequency list for one channel (entry 0 becomes current, every entry starts from a fresh freq_t)
+int abo_scan_configure(void* h, int dev, int chan, int n_freqs, const abo_channel_cfg* freqs) {
+    Oracle* o = (Oracle*)h;
+    if (dev < 0 || dev >= o->ndev() || n_freqs < 1 || !freqs) return -1;
+    Device& d = o->D(dev);
+    if (chan < 0 || chan >= (int)d.ch.size()) return -1;
+    Channel& c = *d.ch[chan];
+    c.freqlist.clear();
+    for (int i = 0; i < n_freqs; i++) c.freqlist.push_back(make_freq(freqs[i], o->wave_rate));
+    c.freq_idx = 0;
+    return 0;
+}
+
+// what controller_thread does to channels[0].freq_idx (rtl_airband.cpp:117-119); takes effect with the next batch (:498)
+int abo_scan_select(void* h, int dev, int chan, int freq_idx) {
+    Oracle* o = (Oracle*)h;
+    if (dev < 0 || dev >= o->ndev()) return -1;
+    Device& d = o->D(dev);
+    if (chan < 0 || chan >= (int)d.ch.size()) return -1;
+    Channel& c = *d.ch[chan];
+    if (freq_idx < 0 || freq_idx >= (int)c.freqlist.size()) return -1;
+    c.freq_idx = freq_idx;
     return 0;
 }
 

@@ -65,6 +65,8 @@ def lib(variant: str = "restated"):
         "abo_fetch_batch": (i, [vp, i, vp, vp, vp]),
         "abo_get_stats": (i, [vp, i, i, C.POINTER(CSquelchStats)]),
         "abo_set_bin": (i, [vp, i, i, i]),
+        "abo_scan_configure": (i, [vp, i, i, i, vp]),
+        "abo_scan_select": (i, [vp, i, i, i]),
         "abo_get_window": (i, [vp, vp]),
         "abo_debug_frame": (i, [vp, i, vp, vp, vp]),
         "abo_calc_bin": (i32, [i32, i32, i32, i32]),
@@ -183,6 +185,15 @@ class Oracle:
         s = CSquelchStats()
         assert self.L.abo_get_stats(self.h, dev, chan, C.byref(s)) == 0
         return s
+
+    def scan_configure(self, dev: int, chan: int, freqs) -> None:
+        """Install a scan-mode frequency list (list of config.Channel); entry 0 becomes current."""
+        from airband_b200.config import channels_to_c
+        arr = channels_to_c(freqs)
+        assert self.L.abo_scan_configure(self.h, dev, chan, len(freqs), C.cast(arr, C.c_void_p)) == 0
+
+    def scan_select(self, dev: int, chan: int, freq_idx: int) -> None:
+        assert self.L.abo_scan_select(self.h, dev, chan, freq_idx) == 0
 
     def window(self) -> np.ndarray:
         w = np.empty(self.cfg.fft_size, np.float32)

@@ -185,6 +185,61 @@ struct Device {
     std::deque<std::pair<int, int>> ready;  // (slot, batch-in-run)
 };
 
+// ---- scan mode: per-frequency freq_t sets (rtl_airband.h:223-233,250-252) ------------------------------------------------
+// A scan channel keeps one FreqSet per freqlist[] entry in device memory.  The live slot (params/state/sqbuf/tone banks
+// of channel g, what K2 reads) holds the current entry; abg_scan_select() swaps entries with one small kernel on the
+// K2 stream, i.e. between the batches of two runs, which is when demodulate() re-reads freq_idx (rtl_airband.cpp:498).
+struct FreqSet {
+    ChanParams p;  // freq-level fields only: modulation, ampfactor, notch, low-pass, CTCSS
+    ChanState s;   // freq-level fields only: Squelch, CTCSS counters, filter delay elements, agcavgfast, active_counter
+    float sqbuf[ABG_SQ_BUF];
+    float tone_coeff[2][ABG_MAX_TONES], tone_q1[2][ABG_MAX_TONES], tone_q2[2][ABG_MAX_TONES], tone_mag[2][ABG_MAX_TONES];
+};
+struct ScanView {
+    ChanParams* params;
+    ChanState* state;
+    float *sqbuf, *tone_coeff, *tone_q1, *tone_q2, *tone_mag;
+    int Gp;
+};
+__device__ void freq_fields_copy(ChanParams& dp, ChanState& ds, const ChanParams& sp, const ChanState& ss) {
+    // channel_t members stay with the channel: dev, needs_raw_iq, has_iq_outputs, dm_dphi, alpha, afc / dm_phi, pr, pj,
+    // prev_waveout, axc_prev
+    dp.modulation = sp.modulation; dp.ampfactor = sp.ampfactor;
+    dp.notch_on = sp.notch_on; dp.nd0 = sp.nd0; dp.nd1 = sp.nd1; dp.nd2 = sp.nd2;
+    dp.lp_on = sp.lp_on; dp.lp_gain = sp.lp_gain; dp.lp_yc0 = sp.lp_yc0; dp.lp_yc1 = sp.lp_yc1;
+    dp.ctcss_on = sp.ctcss_on;
+    for (int w = 0; w < 2; w++) { dp.n_tones[w] = sp.n_tones[w]; dp.window[w] = sp.window[w]; }
+    const uint32_t dm_phi = ds.dm_phi;
+    const float pr = ds.pr, pj = ds.pj, prev_waveout = ds.prev_waveout;
+    const int32_t axc_prev = ds.axc_prev;
+    ds = ss;
+    ds.dm_phi = dm_phi; ds.pr = pr; ds.pj = pj; ds.prev_waveout = prev_waveout; ds.axc_prev = axc_prev;
+}
+__global__ void scan_swap_kernel(const ScanView v, int g, FreqSet* save_to, const FreqSet* load_from) {
+    const int t = threadIdx.x, Gp = v.Gp;
+    if (t == 0) {
+        save_to->p = v.params[g];
+        save_to->s = v.state[g];
+        ChanParams p = v.params[g];
+        ChanState s = v.state[g];
+        freq_fields_copy(p, s, load_from->p, load_from->s);
+        v.params[g] = p;
+        v.state[g] = s;
+    }
+    for (int i = t; i < ABG_SQ_BUF; i += blockDim.x) {
+        save_to->sqbuf[i] = v.sqbuf[(size_t)i * Gp + g];
+        v.sqbuf[(size_t)i * Gp + g] = load_from->sqbuf[i];
+    }
+    for (int i = t; i < 2 * ABG_MAX_TONES; i += blockDim.x) {
+        const int w = i / ABG_MAX_TONES, k = i % ABG_MAX_TONES;
+        const size_t o = (size_t)i * Gp + g;
+        save_to->tone_coeff[w][k] = v.tone_coeff[o]; v.tone_coeff[o] = load_from->tone_coeff[w][k];
+        save_to->tone_q1[w][k] = v.tone_q1[o];       v.tone_q1[o] = load_from->tone_q1[w][k];
+        save_to->tone_q2[w][k] = v.tone_q2[o];       v.tone_q2[o] = load_from->tone_q2[w][k];
+        save_to->tone_mag[w][k] = v.tone_mag[o];     v.tone_mag[o] = load_from->tone_mag[w][k];
+    }
+}
+
 struct Group {
     int sfmt, hop_bytes;
     float fullscale;
@@ -218,6 +273,11 @@ struct abg_engine {
     std::vector<Device> dev;
     std::vector<Group> groups;
     std::vector<ChanParams> h_params;
+    struct ScanChan {
+        int g = 0, n_freqs = 0, cur = 0;
+        FreqSet* stash = nullptr;  // device array [n_freqs]; entry `cur` is stale while it is live
+    };
+    std::vector<ScanChan> scan;
     // device memory
     DevBuf<ChanParams> params;
     DevBuf<ChanState> state;
@@ -287,6 +347,8 @@ void engine_free(abg_engine* e) {
     e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin[0].free(); e->iqin[1].free(); e->iqout.free();
     e->tw1.free(); e->tw2.free(); e->twn.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
     if (e->d_k2) cudaFree(e->d_k2);
+    for (auto& sc : e->scan)
+        if (sc.stash) cudaFree(sc.stash);
     for (auto& s : e->slots) {
         if (s.wout) cudaFreeHost(s.wout);
         if (s.iqout) cudaFreeHost(s.iqout);
@@ -318,6 +380,77 @@ int frames_available(const abg_engine* e, const Device& d, size_t fill, size_t c
     const size_t need = (size_t)d.hop_bytes + (size_t)e->N * d.bpc;
     if (avail < need) return 0;
     return (int)((avail - need) / d.hop_bytes) + 1;
+}
+
+// The freq_t part of one channel as parse_channels() sets it up (config.cpp:437-619): Squelch, NotchFilter,
+// LowpassFilter, CTCSS banks, ampfactor, modulation, agcavgfast.  Used for channels[] at abg_create() and for every
+// entry of a scan-mode frequency list (abg_scan_configure).  Channel-level fields of p / s are left alone.
+int build_freq(int W, const abg_channel_cfg& cc, ChanParams& p, ChanState& s, std::vector<float> banks[2], const char* what) {
+    if (cc.modulation != ABG_MOD_AM && cc.modulation != ABG_MOD_NFM) return fail(ABG_EINVAL, "%s: unknown modulation", what);
+    p.modulation = cc.modulation;
+    p.ampfactor = cc.ampfactor;
+    p.notch_on = p.lp_on = p.ctcss_on = 0;
+    p.n_tones[0] = p.n_tones[1] = 0;
+    banks[0].clear();
+    banks[1].clear();
+    // ---- Squelch::Squelch(), squelch.cpp:36-82 ----
+    s.noise_floor = 5.0f;
+    s.manual = 0;
+    s.normal_ratio = pow(10.0, 9.54f / 20.0);
+    s.flappy_ratio = s.normal_ratio * 0.9f;
+    s.avg_cap = 1.5f * s.normal_ratio * s.noise_floor;
+    s.manual_level = -1.0;
+    s.pre_full = s.pre_capped = s.post_full = s.post_capped = 0.001f;
+    s.level_cache = 0.0f;
+    s.using_post = 0;
+    s.next_state = s.cur_state = SQ_CLOSED;
+    s.delay = 0;
+    s.sample_count_mod16 = 15u;  // sample_count_ = (size_t)-1: the first sample makes it 0 (squelch.cpp:58,204)
+    s.head = 0;
+    // ---- config.cpp:437-515: level first, then SNR ----
+    if (cc.squelch_level > 0) {  // set_squelch_level_threshold, squelch.cpp:84-96
+        s.manual = 1;
+        s.manual_level = cc.squelch_level;
+        s.avg_cap = 1.5f * s.manual_level;
+    }
+    if (cc.squelch_snr_db >= 0) {  // set_squelch_snr_threshold, squelch.cpp:98-108
+        s.manual = 0;
+        s.normal_ratio = pow(10.0, cc.squelch_snr_db / 20.0);
+        s.flappy_ratio = s.normal_ratio * 0.9f;
+        s.avg_cap = 1.5f * s.normal_ratio * s.noise_floor;
+    }
+    // ---- NotchFilter, filters.cpp:30-47 ----
+    if (cc.notch_hz > 0) {
+        float sample_freq = W, q = cc.notch_q;
+        float wo = 2 * M_PI * (cc.notch_hz / sample_freq);
+        float en = 1 / (1 + tan(wo / (q * 2)));
+        float pn = cos(wo);
+        p.notch_on = 1;
+        p.nd0 = en;
+        p.nd1 = 2 * en * pn;
+        p.nd2 = (2 * en - 1);
+    }
+    // ---- LowpassFilter, filters.cpp:67-96 ----
+    if (cc.lowpass_hz > 0) {
+        if (!lowpass_design(cc.lowpass_hz, (float)W, &p.lp_gain, &p.lp_yc0, &p.lp_yc1))
+            return fail(ABG_EINVAL, "%s: lowpass design failed (poles not conjugate)", what);
+        p.lp_on = 1;
+    }
+    // ---- CTCSS, squelch.cpp:110-116 ----
+    if (cc.ctcss_hz > 0) {
+        const float sr = W;
+        p.ctcss_on = 1;
+        p.window[0] = sr * 0.05;
+        p.window[1] = sr * 0.4;
+        for (int w = 0; w < 2; w++) {
+            std::vector<float> bank = tone_bank(cc.ctcss_hz, sr, p.window[w]);
+            if ((int)bank.size() > ABG_MAX_TONES) return fail(ABG_EINVAL, "CTCSS bank too large");
+            p.n_tones[w] = (int)bank.size();
+            banks[w] = bank;
+        }
+    }
+    s.agcavgfast = 0.5f;  // mk_freqlist / parse_channels, config.cpp:265-281
+    return ABG_OK;
 }
 
 int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
@@ -378,78 +511,27 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
             const abg_channel_cfg& cc = dc.channels[c];
             const int g = d.g0 + c;
             if (cc.bin < 0 || cc.bin >= N) return fail(ABG_EINVAL, "devices[%d].channels[%d]: bin %d outside 0..%d", i, c, cc.bin, N - 1);
-            if (cc.modulation != ABG_MOD_AM && cc.modulation != ABG_MOD_NFM) return fail(ABG_EINVAL, "devices[%d].channels[%d]: unknown modulation", i, c);
             ChanParams& p = hp[g];
             ChanState& s = hs[g];
             hb[g] = cc.bin;
             p.dev = i;
-            p.modulation = cc.modulation;
             p.needs_raw_iq = cc.needs_raw_iq ? 1 : 0;
             p.has_iq_outputs = cc.has_iq_outputs ? 1 : 0;
             if (p.has_iq_outputs) e->any_iq_out = true;
             p.dm_dphi = cc.dm_dphi;
             p.alpha = cc.alpha;
-            p.ampfactor = cc.ampfactor;
             p.afc = cc.afc & 0xff;
             if (p.afc) d.has_afc = true;
-            // ---- Squelch::Squelch(), squelch.cpp:36-82 ----
-            s.noise_floor = 5.0f;
-            s.manual = 0;
-            s.normal_ratio = pow(10.0, 9.54f / 20.0);
-            s.flappy_ratio = s.normal_ratio * 0.9f;
-            s.avg_cap = 1.5f * s.normal_ratio * s.noise_floor;
-            s.manual_level = -1.0;
-            s.pre_full = s.pre_capped = s.post_full = s.post_capped = 0.001f;
-            s.level_cache = 0.0f;
-            s.using_post = 0;
-            s.next_state = s.cur_state = SQ_CLOSED;
-            s.delay = 0;
-            s.sample_count_mod16 = 15u;  // sample_count_ = (size_t)-1: the first sample makes it 0 (squelch.cpp:58,204)
-            s.head = 0;
-            // ---- config.cpp:437-515: level first, then SNR ----
-            if (cc.squelch_level > 0) {  // set_squelch_level_threshold, squelch.cpp:84-96
-                s.manual = 1;
-                s.manual_level = cc.squelch_level;
-                s.avg_cap = 1.5f * s.manual_level;
-            }
-            if (cc.squelch_snr_db >= 0) {  // set_squelch_snr_threshold, squelch.cpp:98-108
-                s.manual = 0;
-                s.normal_ratio = pow(10.0, cc.squelch_snr_db / 20.0);
-                s.flappy_ratio = s.normal_ratio * 0.9f;
-                s.avg_cap = 1.5f * s.normal_ratio * s.noise_floor;
-            }
-            // ---- NotchFilter, filters.cpp:30-47 ----
-            if (cc.notch_hz > 0) {
-                float sample_freq = e->W, q = cc.notch_q;
-                float wo = 2 * M_PI * (cc.notch_hz / sample_freq);
-                float en = 1 / (1 + tan(wo / (q * 2)));
-                float pn = cos(wo);
-                p.notch_on = 1;
-                p.nd0 = en;
-                p.nd1 = 2 * en * pn;
-                p.nd2 = (2 * en - 1);
-            }
-            // ---- LowpassFilter, filters.cpp:67-96 ----
-            if (cc.lowpass_hz > 0) {
-                if (!lowpass_design(cc.lowpass_hz, (float)e->W, &p.lp_gain, &p.lp_yc0, &p.lp_yc1))
-                    return fail(ABG_EINVAL, "devices[%d].channels[%d]: lowpass design failed (poles not conjugate)", i, c);
-                p.lp_on = 1;
-            }
-            // ---- CTCSS, squelch.cpp:110-116 ----
-            if (cc.ctcss_hz > 0) {
-                const float sr = e->W;
-                p.ctcss_on = 1;
-                p.window[0] = sr * 0.05;
-                p.window[1] = sr * 0.4;
-                for (int w = 0; w < 2; w++) {
-                    std::vector<float> bank = tone_bank(cc.ctcss_hz, sr, p.window[w]);
-                    if ((int)bank.size() > ABG_MAX_TONES) return fail(ABG_EINVAL, "CTCSS bank too large");
-                    p.n_tones[w] = (int)bank.size();
-                    for (size_t t = 0; t < bank.size(); t++) h_coeff[((size_t)w * ABG_MAX_TONES + t) * Gp + g] = bank[t];
-                }
+            {
+                char what[64];
+                snprintf(what, sizeof(what), "devices[%d].channels[%d]", i, c);
+                std::vector<float> banks[2];
+                const int rc = build_freq(e->W, cc, p, s, banks, what);
+                if (rc != ABG_OK) return rc;
+                for (int w = 0; w < 2; w++)
+                    for (size_t t = 0; t < banks[w].size(); t++) h_coeff[((size_t)w * ABG_MAX_TONES + t) * Gp + g] = banks[w][t];
             }
             // ---- mk_freqlist / parse_channels initial values, config.cpp:265-281,313-331 ----
-            s.agcavgfast = 0.5f;
             s.dm_phi = 0;
             s.pr = s.pj = 0.0f;
             s.prev_waveout = 0.5f;
@@ -979,6 +1061,76 @@ int abg_set_bin(abg_engine* e, int dev, int chan, int bin) {
     CU(cudaMemcpyAsync(e->bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->base_bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    return ABG_OK;
+}
+
+// ---- scan mode -------------------------------------------------------------------------------------------------------
+static ScanView scan_view(abg_engine* e) {
+    ScanView v;
+    v.params = e->params.p; v.state = e->state.p; v.sqbuf = e->sqbuf.p; v.tone_coeff = e->tone_coeff.p;
+    v.tone_q1 = e->tone_q1.p; v.tone_q2 = e->tone_q2.p; v.tone_mag = e->tone_mag.p; v.Gp = e->Gp;
+    return v;
+}
+
+int abg_scan_configure(abg_engine* e, int dev, int chan, int n_freqs, const abg_channel_cfg* freqs) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_scan_configure: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    if (chan < 0 || chan >= d.C) return fail(ABG_ERANGE, "abg_scan_configure: channel %d out of range", chan);
+    if (n_freqs < 1 || !freqs) return fail(ABG_EINVAL, "abg_scan_configure: empty frequency list");
+    const int g = d.g0 + chan;
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
+    std::vector<FreqSet> sets((size_t)n_freqs);
+    for (int i = 0; i < n_freqs; i++) {
+        FreqSet& f = sets[i];
+        memset(&f, 0, sizeof(f));
+        char what[64];
+        snprintf(what, sizeof(what), "abg_scan_configure: freqs[%d]", i);
+        std::vector<float> banks[2];
+        const int rc = build_freq(e->W, freqs[i], f.p, f.s, banks, what);
+        if (rc != ABG_OK) return rc;
+        for (int w = 0; w < 2; w++)
+            for (size_t t = 0; t < banks[w].size(); t++) f.tone_coeff[w][t] = banks[w][t];
+    }
+    abg_engine::ScanChan* sc = nullptr;
+    for (auto& x : e->scan)
+        if (x.g == g) sc = &x;
+    if (!sc) {
+        e->scan.emplace_back();
+        sc = &e->scan.back();
+        sc->g = g;
+    }
+    if (sc->stash) cudaFree(sc->stash);
+    sc->stash = nullptr;
+    // one extra entry: scratch that receives the state being replaced below
+    if (cudaMalloc((void**)&sc->stash, sizeof(FreqSet) * (size_t)(n_freqs + 1)) != cudaSuccess) return fail(ABG_ENOMEM, "Out of device memory for the scan frequency list");
+    CU(cudaMemcpy(sc->stash, sets.data(), sizeof(FreqSet) * (size_t)n_freqs, cudaMemcpyHostToDevice));
+    sc->n_freqs = n_freqs;
+    sc->cur = 0;
+    scan_swap_kernel<<<1, 128, 0, e->stream_b>>>(scan_view(e), g, sc->stash + n_freqs, sc->stash + 0);  // entry 0 goes live, fresh
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream_b));
+    return ABG_OK;
+}
+
+int abg_scan_select(abg_engine* e, int dev, int chan, int freq_idx) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_scan_select: device %d out of range", dev);
+    Device& d = e->dev[dev];
+    if (chan < 0 || chan >= d.C) return fail(ABG_ERANGE, "abg_scan_select: channel %d out of range", chan);
+    const int g = d.g0 + chan;
+    abg_engine::ScanChan* sc = nullptr;
+    for (auto& x : e->scan)
+        if (x.g == g) sc = &x;
+    if (!sc) return fail(ABG_EINVAL, "abg_scan_select: devices[%d].channels[%d] has no frequency list (abg_scan_configure)", dev, chan);
+    if (freq_idx < 0 || freq_idx >= sc->n_freqs) return fail(ABG_ERANGE, "abg_scan_select: frequency index %d outside 0..%d", freq_idx, sc->n_freqs - 1);
+    if (freq_idx == sc->cur) return ABG_OK;
+    cudaSetDevice(e->cuda_dev);
+    // stream B: after every K2 already enqueued, before the next one = between two batches (rtl_airband.cpp:498)
+    scan_swap_kernel<<<1, 128, 0, e->stream_b>>>(scan_view(e), g, sc->stash + sc->cur, sc->stash + freq_idx);
+    CU(cudaGetLastError());
+    e->launches++;
+    sc->cur = freq_idx;
     return ABG_OK;
 }
 

@@ -55,6 +55,27 @@ static void fatal(const char* what) {
     g_b200.do_exit = 1;                          // error() = _Exit(1) there; the test harness wants to survive
 }
 
+// channel_t / freq_t -> abg_channel_cfg (what INTEGRATION.md calls b200_channel_cfg)
+static void fill_channel_cfg(const device_t* dev, int c, const freq_t* f, abg_channel_cfg* out) {
+    const channel_t* ch = dev->channels + c;
+    abg_channel_cfg& o = *out;
+    memset(&o, 0, sizeof(o));
+    o.bin = (int32_t)dev->bins[c];
+    o.modulation = f->modulation == MOD_NFM ? ABG_MOD_NFM : ABG_MOD_AM;
+    o.needs_raw_iq = ch->needs_raw_iq;
+    o.has_iq_outputs = ch->has_iq_outputs;
+    o.dm_dphi = ch->dm_dphi;
+    o.alpha = ch->alpha;
+    o.ampfactor = f->ampfactor;
+    o.squelch_level = f->squelch_level;
+    o.squelch_snr_db = f->squelch_snr_db;
+    o.lowpass_hz = f->lowpass_hz;
+    o.notch_hz = f->notch_hz;
+    o.notch_q = f->notch_q;
+    o.ctcss_hz = f->ctcss_hz;
+    o.afc = ch->afc;
+}
+
 extern "C" void* demodulate_b200(void* params) {
     demod_params_t* dp = (demod_params_t*)params;
     const int d0 = dp->device_start, d1 = dp->device_end, nd = d1 - d0;
@@ -69,23 +90,7 @@ extern "C" void* demodulate_b200(void* params) {
         ccfg[i].resize(dev->channel_count);
         for (int c = 0; c < dev->channel_count; c++) {
             channel_t* ch = dev->channels + c;
-            freq_t* f = ch->freqlist + ch->freq_idx;
-            abg_channel_cfg& o = ccfg[i][c];
-            memset(&o, 0, sizeof(o));
-            o.bin = (int32_t)dev->bins[c];
-            o.modulation = f->modulation == MOD_NFM ? ABG_MOD_NFM : ABG_MOD_AM;
-            o.needs_raw_iq = ch->needs_raw_iq;
-            o.has_iq_outputs = ch->has_iq_outputs;
-            o.dm_dphi = ch->dm_dphi;
-            o.alpha = ch->alpha;
-            o.ampfactor = f->ampfactor;
-            o.squelch_level = f->squelch_level;
-            o.squelch_snr_db = f->squelch_snr_db;
-            o.lowpass_hz = f->lowpass_hz;
-            o.notch_hz = f->notch_hz;
-            o.notch_q = f->notch_q;
-            o.ctcss_hz = f->ctcss_hz;
-            o.afc = ch->afc;
+            fill_channel_cfg(dev, c, ch->freqlist + ch->freq_idx, &ccfg[i][c]);
         }
         dcfg[i].sfmt = (int32_t)dev->input->sfmt;
         dcfg[i].fullscale = dev->input->fullscale;
@@ -108,6 +113,25 @@ extern "C" void* demodulate_b200(void* params) {
     if (abg_create(&cfg, &opt, &eng) != ABG_OK) {
         fatal("Unable to start the B200 demodulation engine");
         return NULL;
+    }
+    // ---- scan mode: channels with a frequency list (rtl_airband.h:250-252) hand the whole list to the engine; the entry
+    // in use follows channel_t.freq_idx, which controller_thread changes (rtl_airband.cpp:117-119) ----
+    std::vector<std::vector<int>> scan_idx(nd);  // freq_idx the engine currently uses, -1 = not a scan channel
+    for (int i = 0; i < nd; i++) {
+        device_t* dev = devices + d0 + i;
+        scan_idx[i].assign(dev->channel_count, -1);
+        for (int c = 0; c < dev->channel_count; c++) {
+            channel_t* ch = dev->channels + c;
+            if (ch->freq_count < 2) continue;
+            std::vector<abg_channel_cfg> list(ch->freq_count);
+            for (int k = 0; k < ch->freq_count; k++) fill_channel_cfg(dev, c, ch->freqlist + k, &list[k]);
+            if (abg_scan_configure(eng, i, c, ch->freq_count, list.data()) != ABG_OK) {
+                fatal("abg_scan_configure failed");
+                abg_destroy(eng);
+                return NULL;
+            }
+            scan_idx[i][c] = 0;
+        }
     }
     std::vector<float> wo, iq;
     std::vector<char> axc;
@@ -156,6 +180,19 @@ extern "C" void* demodulate_b200(void* params) {
                 in->bufs = (in->bufs + chunk) % in->buf_size;  // not under the lock, like :669
                 n -= chunk;
                 pushed = true;
+            }
+        }
+        for (int i = 0; i < nd; i++) {  // fparms = freqlist + freq_idx, re-read before every batch (:498)
+            device_t* dev = devices + d0 + i;
+            for (int c = 0; c < dev->channel_count; c++) {
+                const int want = dev->channels[c].freq_idx;
+                if (scan_idx[i][c] < 0 || want == scan_idx[i][c]) continue;
+                if (abg_scan_select(eng, i, c, want) != ABG_OK) {
+                    fatal("abg_scan_select failed");
+                    abg_destroy(eng);
+                    return NULL;
+                }
+                scan_idx[i][c] = want;
             }
         }
         int produced = abg_run(eng, -1);

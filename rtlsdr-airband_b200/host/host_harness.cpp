@@ -61,6 +61,7 @@ struct Harness {
     std::vector<input_t> inputs;
     std::vector<std::vector<channel_t>> chans;
     std::vector<std::vector<freq_t>> freqs;
+    std::vector<std::vector<freq_t>> scan_lists;  // frequency lists installed with abh_set_freqlist
     std::vector<std::vector<size_t>> bins, base_bins;
     std::vector<std::vector<float>> bufs_wave, bufs_iq;
     std::vector<std::vector<unsigned char>> rings;
@@ -174,6 +175,30 @@ ABG_API void* abh_create(const abg_config* cfg, int max_batches_per_run) {
     return h;
 }
 
+// scan mode: give devices[dev].channels[chan] a frequency list (freq_t part of every entry from freqs[]) and the entry
+// controller_thread would have selected; call before abh_run
+ABG_API int abh_set_freqlist(void* hp, int dev, int chan, int n_freqs, const abg_channel_cfg* freqs, int freq_idx) {
+    Harness* h = (Harness*)hp;
+    if (dev < 0 || dev >= (int)h->devs.size() || chan < 0 || chan >= h->devs[dev].channel_count || n_freqs < 1 || freq_idx < 0 || freq_idx >= n_freqs) return -1;
+    h->scan_lists.emplace_back((size_t)n_freqs);
+    std::vector<freq_t>& list = h->scan_lists.back();
+    for (int k = 0; k < n_freqs; k++) {
+        const abg_channel_cfg& cc = freqs[k];
+        freq_t& f = list[k];
+        memset(&f, 0, sizeof(f));
+        f.agcavgfast = 0.5f;
+        f.ampfactor = cc.ampfactor;
+        f.modulation = cc.modulation == ABG_MOD_NFM ? MOD_NFM : MOD_AM;
+        f.squelch_level = cc.squelch_level; f.squelch_snr_db = cc.squelch_snr_db; f.notch_hz = cc.notch_hz; f.notch_q = cc.notch_q;
+        f.ctcss_hz = cc.ctcss_hz; f.lowpass_hz = cc.lowpass_hz;
+    }
+    channel_t& ch = h->chans[dev][chan];
+    ch.freqlist = list.data();
+    ch.freq_count = n_freqs;
+    ch.freq_idx = freq_idx;
+    return 0;
+}
+
 // feed one raw stream per device through the rings, demodulate with demodulate_b200(), consume; returns 0 on success
 ABG_API int abh_run(void* hp, const unsigned char* const* raws, const size_t* raw_bytes, int timeout_s) {
     Harness* h = (Harness*)hp;
@@ -227,7 +252,10 @@ ABG_API const float* abh_iq_out(void* hp, int dev) { return ((Harness*)hp)->out_
 ABG_API const char* abh_axc(void* hp, int dev) { return ((Harness*)hp)->out_axc[dev].data(); }
 ABG_API size_t abh_overflows(void* hp, int dev) { return ((Harness*)hp)->inputs[dev].overflow_count; }
 ABG_API size_t abh_overruns(void* hp, int dev) { return ((Harness*)hp)->devs[dev].output_overrun_count; }
-ABG_API size_t abh_active_counter(void* hp, int dev, int chan) { return ((Harness*)hp)->freqs[dev][chan].active_counter; }
+ABG_API size_t abh_active_counter(void* hp, int dev, int chan) {
+    const channel_t& ch = ((Harness*)hp)->chans[dev][chan];
+    return ch.freqlist[ch.freq_idx].active_counter;
+}
 ABG_API const char* abh_last_error(void) { return g_b200.last_error; }
 ABG_API void abh_destroy(void* hp) { delete (Harness*)hp; }
 

@@ -158,6 +158,18 @@ class Device:
         return BYTES_PER_SAMPLE[self.sfmt]
 
 
+def channels_to_c(channels):
+    """ctypes array of abg_channel_cfg / abo_channel_cfg for a list of Channel (also used for scan-mode frequency lists)."""
+    chans = (CChannelCfg * len(channels))()
+    for j, c in enumerate(channels):
+        cc = chans[j]
+        cc.bin, cc.modulation, cc.needs_raw_iq, cc.has_iq_outputs = c.bin, c.modulation, c.needs_raw_iq, c.has_iq_outputs
+        cc.dm_dphi, cc.alpha, cc.ampfactor = c.dm_dphi & 0xFFFFFFFF, c.alpha, c.ampfactor
+        cc.squelch_level, cc.squelch_snr_db = c.squelch_level, c.squelch_snr_db
+        cc.lowpass_hz, cc.notch_hz, cc.notch_q, cc.ctcss_hz, cc.afc = c.lowpass_hz, c.notch_hz, c.notch_q, c.ctcss_hz, c.afc
+    return chans
+
+
 @dataclass
 class Config:
     fft_size: int = 512
@@ -177,13 +189,7 @@ class Config:
         keep = []
         devs = (CDeviceCfg * len(self.devices))()
         for i, d in enumerate(self.devices):
-            chans = (CChannelCfg * len(d.channels))()
-            for j, c in enumerate(d.channels):
-                cc = chans[j]
-                cc.bin, cc.modulation, cc.needs_raw_iq, cc.has_iq_outputs = c.bin, c.modulation, c.needs_raw_iq, c.has_iq_outputs
-                cc.dm_dphi, cc.alpha, cc.ampfactor = c.dm_dphi & 0xFFFFFFFF, c.alpha, c.ampfactor
-                cc.squelch_level, cc.squelch_snr_db = c.squelch_level, c.squelch_snr_db
-                cc.lowpass_hz, cc.notch_hz, cc.notch_q, cc.ctcss_hz, cc.afc = c.lowpass_hz, c.notch_hz, c.notch_q, c.ctcss_hz, c.afc
+            chans = channels_to_c(d.channels)
             keep.append(chans)
             devs[i].sfmt, devs[i].fullscale, devs[i].sample_rate = d.sfmt, d.fullscale, d.sample_rate
             devs[i].n_channels = len(d.channels)

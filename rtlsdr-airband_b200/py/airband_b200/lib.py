@@ -22,7 +22,7 @@ SYMBOLS = [
     "abg_last_error", "abg_version", "abg_create", "abg_destroy", "abg_wave_batch", "abg_hop", "abg_push",
     "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_fetch_batches", "abg_get_stats", "abg_set_bin",
     "abg_resident_load", "abg_run_resident", "abg_set_stream", "abg_launch_count", "abg_mixers_configure",
-    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline",
+    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline", "abg_scan_configure", "abg_scan_select",
 ]
 
 
@@ -84,6 +84,8 @@ def load():
     L.abg_mixer_device_buffers.restype, L.abg_mixer_device_buffers.argtypes = i, [vp, C.POINTER(vp), C.POINTER(vp)]
     L.abg_debug_frame.restype, L.abg_debug_frame.argtypes = i, [vp, i, vp, vp]
     L.abg_last_run_times.restype, L.abg_last_run_times.argtypes = i, [vp, C.POINTER(C.c_float)]
+    L.abg_scan_configure.restype, L.abg_scan_configure.argtypes = i, [vp, i, i, i, vp]
+    L.abg_scan_select.restype, L.abg_scan_select.argtypes = i, [vp, i, i, i]
     L.abg_debug_timeline.restype, L.abg_debug_timeline.argtypes = i, [vp, i, C.POINTER(C.c_float)]
     _LIB = L
     return L
@@ -211,6 +213,15 @@ class Engine:
         a = (C.c_float * (5 * n_runs))()
         self._chk(self.L.abg_debug_timeline(self.h, n_runs, a))
         return np.array(a, dtype=np.float32).reshape(n_runs, 5)
+
+    def scan_configure(self, dev: int, chan: int, freqs) -> None:
+        """Install a scan-mode frequency list (list of config.Channel); entry 0 becomes current."""
+        from .config import channels_to_c
+        arr = channels_to_c(freqs)
+        self._chk(self.L.abg_scan_configure(self.h, dev, chan, len(freqs), C.cast(arr, C.c_void_p)))
+
+    def scan_select(self, dev: int, chan: int, freq_idx: int) -> None:
+        self._chk(self.L.abg_scan_select(self.h, dev, chan, freq_idx))
 
     def launch_count(self) -> int:
         return int(self.L.abg_launch_count(self.h))

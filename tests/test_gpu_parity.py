@@ -279,3 +279,82 @@ def test_error_codes():
         e.push(0, big)
     assert ei.value.code == -6
     assert e.fetch(0) is None and e.run(-1) == 0
+
+
+def _scan_setup():
+    """One scan device (one channel, rtl_airband.h:265 R_SCAN) with three freqlist[] entries that differ in everything a
+    freq_t owns: manual-squelch AM, auto-squelch AM with another ampfactor and a notch, NFM with CTCSS."""
+    sr, n, w, cf = 2560000, 1024, 16000, 120000000
+    f0 = cf + 250000
+    base = cm.make_channel(f0, cf, sr, n, w, modulation=cm.MOD_NFM, bandwidth=6000, squelch_dbfs=-35.0)   # needs_raw_iq as scan+NFM builds have
+    freqs = [
+        cm.make_channel(f0, cf, sr, n, w, modulation=cm.MOD_AM, bandwidth=6000, squelch_dbfs=-35.0),
+        cm.make_channel(f0, cf, sr, n, w, modulation=cm.MOD_AM, bandwidth=6000, ampfactor=2.5, notch_hz=1000.0, squelch_snr_db=6.0),
+        cm.make_channel(f0, cf, sr, n, w, modulation=cm.MOD_NFM, bandwidth=6000, squelch_dbfs=-35.0, ctcss_hz=100.0, ampfactor=1.5),
+    ]
+    base.synth_ctcss_hz = 100.0  # the synthetic FM signal carries the sub-tone entry 2 listens for
+    cfg = cm.Config(fft_size=n, wave_rate=w, devices=[cm.Device(sample_rate=sr, sfmt=cm.SFMT_S16, centerfreq=cf, channels=[base])])
+    return cfg, freqs
+
+
+def test_scan_mode_frequency_list_matches_oracle():
+    """controller_thread switches freq_idx between batches (rtl_airband.cpp:117-119,498); every entry keeps its own
+    Squelch / filters / AGC / counters across visits."""
+    cfg, freqs = _scan_setup()
+    nb_per_visit, visits = 4, [0, 1, 2, 1, 0, 2, 2, 0]
+    total = nb_per_visit * len(visits)
+    raw = wl.synth_iq(cfg, 0, wl.samples_for_batches(cfg, 0, total), key_on_s=1.2, key_off_s=0.2, amplitude=0.2)
+    hop = cfg.hop(0)
+    B = cfg.wave_batch
+    o = op.Oracle(cfg)
+    e = lib.Engine(cfg, max_batches_per_run=nb_per_visit, input_capacity_batches=2 * nb_per_visit + 1)
+    o.scan_configure(0, 0, freqs)
+    e.scan_configure(0, 0, freqs)
+    pos = 0
+    for k, idx in enumerate(visits):
+        need = wl.samples_for_batches(cfg, 0, nb_per_visit * (k + 1)) * 2    # items (I and Q) needed up to the end of this visit
+        chunk = raw[pos:need]
+        pos = need
+        o.scan_select(0, 0, idx)
+        e.scan_select(0, 0, idx)
+        o.push(0, chunk)
+        e.push(0, chunk)
+        assert o.run(nb_per_visit) == nb_per_visit
+        assert e.run(nb_per_visit) == nb_per_visit
+        ow, oi, oa = o.fetch_all(0)
+        outs = [e.fetch(0) for _ in range(nb_per_visit)]
+        gw = np.concatenate([x[0] for x in outs], 1)
+        ga = np.stack([x[2] for x in outs])
+        assert gw.shape == ow.shape == (1, nb_per_visit * B)
+        assert np.array_equal(ga, oa), (k, idx)
+        assert gate(gw, ow) <= TOL, (k, idx, gate(gw, ow))
+        gs, os_ = e.stats(0, 0), o.stats(0, 0)      # getters of the CURRENT entry
+        for f in ("open_count", "flappy_count", "ctcss_count", "no_ctcss_count", "active_counter", "dm_phi"):
+            assert getattr(gs, f) == getattr(os_, f), (k, idx, f, getattr(gs, f), getattr(os_, f))
+        for f in ("noise_level", "signal_level", "squelch_level", "agcavgfast"):
+            a, b = getattr(gs, f), getattr(os_, f)
+            assert abs(a - b) <= 1e-4 * max(1.0, abs(a), abs(b)), (k, idx, f, a, b)
+    # error behaviour
+    with pytest.raises(lib.AbgError):
+        e.scan_select(0, 0, 3)
+    e.close()
+    o.close()
+
+
+def test_host_adapter_scan_channel_uses_the_selected_entry():
+    """demodulate_b200() hands a channel's freqlist[] to the engine and follows channel_t.freq_idx (here fixed to entry 2
+    before the thread starts, as controller_thread would have left it)."""
+    from airband_b200 import host
+    cfg, freqs = _scan_setup()
+    nb = 6
+    raw = wl.synth_iq(cfg, 0, wl.samples_for_batches(cfg, 0, nb), key_on_s=1.2, key_off_s=0.2, amplitude=0.2)
+    o = op.Oracle(cfg)
+    o.scan_configure(0, 0, freqs)
+    o.scan_select(0, 0, 2)
+    o.push(0, raw)
+    assert o.run(-1) == nb
+    ow, oi, oa = o.fetch_all(0)
+    gw, gi, ga, info = host.run_host_pipeline(cfg, [raw], freqlists=[(0, 0, freqs, 2)])[0]
+    assert gw.shape == ow.shape and np.array_equal(ga, oa)
+    assert gate(gw, ow) <= TOL
+    assert info["active"] == [int(np.sum(oa[:, 0] != ord(' ')))]
