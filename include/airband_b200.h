@@ -167,6 +167,15 @@ ABG_API uint64_t abg_launch_count(const abg_engine* e);
 /* Device time of the most recent run, from CUDA events recorded on the engine's stream around its kernels:
  * ms4[0] = K1 (convert+window+FFT+bins, all groups), ms4[1] = K2 (demodulation), ms4[2] = mixers + result copies + tail
  * copy, ms4[3] = whole run.  Waits for that run to finish. */
+/* Optional: page-lock a host buffer that abg_push will be fed from (in the reference: input_t.buffer, the ring filled by
+   the SDR threads, src/input-helpers.cpp:27-36; buf_size + 2*bytes_per_sample*fft_size bytes) so the host->device copies
+   are asynchronous DMA.  Unregister before freeing the buffer. */
+ABG_API int abg_host_register(void* ptr, size_t nbytes);
+ABG_API int abg_host_unregister(void* ptr);
+/* Returns once every abg_push so far has been read out of the caller's memory (with page-locked memory the copies are
+   asynchronous): call it before letting a producer overwrite ring space that was pushed from.  Does not wait for kernels. */
+ABG_API int abg_ingest_sync(abg_engine* e);
+
 /* Scan mode.  Reference: an R_SCAN device has one channel with freqlist[freq_count] (src/rtl_airband.h:250-252); every
    freq_t owns its Squelch, NotchFilter, LowpassFilter, agcavgfast, ampfactor, modulation and active_counter
    (src/rtl_airband.h:223-233).  controller_thread switches channels[0].freq_idx and retunes the input

@@ -1134,6 +1134,41 @@ int abg_scan_select(abg_engine* e, int dev, int chan, int freq_idx) {
     return ABG_OK;
 }
 
+// Pin (page-lock) a host buffer the caller keeps pushing from - in the reference that is input_t.buffer, the ring the
+// SDR driver threads fill (input-helpers.cpp:27-36) - so that abg_push's host->device copies are real asynchronous DMA
+// instead of being staged through the driver's bounce buffer.  Optional: abg_push works with pageable memory too.
+int abg_host_register(void* ptr, size_t nbytes) {
+    if (!ptr || nbytes == 0) return fail(ABG_EINVAL, "abg_host_register: empty range");
+    cudaError_t er = cudaHostRegister(ptr, nbytes, cudaHostRegisterPortable);
+    if (er == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return ABG_OK;
+    }
+    if (er != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ABG_ECUDA, "abg_host_register: %s", cudaGetErrorString(er));
+    }
+    return ABG_OK;
+}
+
+// Returns once every abg_push so far has been read out of the caller's buffers (needed before reusing page-locked
+// memory that was pushed from: with abg_host_register the copies are asynchronous).  Does not wait for kernels.
+int abg_ingest_sync(abg_engine* e) {
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream_c));
+    return ABG_OK;
+}
+
+int abg_host_unregister(void* ptr) {
+    if (!ptr) return ABG_OK;
+    cudaError_t er = cudaHostUnregister(ptr);
+    if (er != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ABG_ECUDA, "abg_host_unregister: %s", cudaGetErrorString(er));
+    }
+    return ABG_OK;
+}
+
 int abg_resident_load(abg_engine* e, int dev, const void* iq, size_t nbytes) {
     if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_resident_load: device %d out of range", dev);
     Device& d = e->dev[dev];

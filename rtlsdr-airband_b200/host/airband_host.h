@@ -24,8 +24,10 @@ typedef enum { INPUT_UNKNOWN = 0, INPUT_INITIALIZED, INPUT_RUNNING, INPUT_FAILED
 enum status { NO_SIGNAL = ' ', SIGNAL = '*', AFC_UP = '<', AFC_DOWN = '>' };  // rtl_airband.h:101
 enum modulations { MOD_AM, MOD_NFM };                                          // rtl_airband.h:193-199
 
+typedef struct input_t input_t;
 struct input_t {
     unsigned char* buffer;  // buf_size + 2 * bytes_per_sample * fft_size bytes (wrap tail, input-helpers.cpp:27-36)
+    void* dev_data;         // plugin-private (input-common.h:41)
     size_t buf_size, bufs, bufe;
     size_t overflow_count;
     input_state_t state;
@@ -34,8 +36,26 @@ struct input_t {
     int bytes_per_sample;
     int sample_rate;
     int centerfreq;
+    // plugin entry points (input-common.h:50-54; parse_config is libconfig++-typed and not mirrored)
+    int (*init)(input_t* const input);
+    void* (*run_rx_thread)(void* input_ptr);  // to be launched via pthread_create()
+    int (*set_centerfreq)(input_t* const input, int const centerfreq);
+    int (*stop)(input_t* const input);
+    pthread_t rx_thread;
     pthread_mutex_t buffer_lock;
 };
+
+// "pattern" input plugin (host/input_pattern.cpp): replays a block of ring-format bytes, paced like a live SDR or
+// lossless like input-file.cpp.  Found by input_new("pattern") in the reference tree (input-common.cpp:35-54 looks up
+// <type>_input_new with dlsym).
+struct pattern_dev_data_t {
+    const unsigned char* block;  // whole complex samples
+    size_t block_len;
+    long repeat;                 // the block is sent this many times, then the input reports INPUT_FAILED (end of stream)
+    double speedup;              // > 0: paced by the wall clock at speedup x sample_rate, never waits (a full ring
+                                 // overflows, input-helpers.cpp:56-60); 0: as fast as the ring drains, lossless
+};
+extern "C" ABG_API input_t* pattern_input_new(void);
 
 class Signal {  // rtl_airband.h:201-221
    public:

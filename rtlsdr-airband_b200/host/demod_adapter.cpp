@@ -114,6 +114,20 @@ extern "C" void* demodulate_b200(void* params) {
         fatal("Unable to start the B200 demodulation engine");
         return NULL;
     }
+    // ---- ingest bridge: pin the input rings in place so that abg_push is asynchronous DMA straight out of the ring the
+    // SDR threads fill (ring + wrap tail, input-helpers.cpp:27-36).  Best effort: pageable rings still work. ----
+    std::vector<unsigned char*> pinned_rings;
+    for (int i = 0; i < nd; i++) {
+        input_t* in = devices[d0 + i].input;
+        const size_t ring_bytes = in->buf_size + 2 * (size_t)in->bytes_per_sample * g_b200.fft_size;
+        if (abg_host_register(in->buffer, ring_bytes) == ABG_OK) pinned_rings.push_back(in->buffer);
+    }
+    struct Unpin {
+        std::vector<unsigned char*>& v;
+        ~Unpin() {
+            for (unsigned char* p : v) abg_host_unregister(p);
+        }
+    } unpin{pinned_rings};
     // ---- scan mode: channels with a frequency list (rtl_airband.h:250-252) hand the whole list to the engine; the entry
     // in use follows channel_t.freq_idx, which controller_thread changes (rtl_airband.cpp:117-119) ----
     std::vector<std::vector<int>> scan_idx(nd);  // freq_idx the engine currently uses, -1 = not a scan channel
@@ -146,6 +160,7 @@ extern "C" void* demodulate_b200(void* params) {
             continue;
         }
         bool pushed = false;
+        std::vector<size_t> new_bufs(nd);
         for (int i = 0; i < nd; i++) {
             device_t* dev = devices + d0 + i;
             input_t* in = dev->input;
@@ -168,19 +183,23 @@ extern "C" void* demodulate_b200(void* params) {
             // hand over whole hops only (the reference advances bufs hop by hop, :669), at most one batch per visit
             size_t n = std::min(available / hop_bytes, (size_t)B) * hop_bytes;
             if (in->state != INPUT_RUNNING && n == 0 && available >= bpc) n = (available / bpc) * bpc;  // final partial hop at EOF
+            size_t local_bufs = in->bufs;
             while (n > 0) {
-                const size_t chunk = std::min(n, in->buf_size - in->bufs);  // up to the physical end of the ring
-                int rc = abg_push(eng, i, in->buffer + in->bufs, chunk);
+                const size_t chunk = std::min(n, in->buf_size - local_bufs);  // up to the physical end of the ring
+                int rc = abg_push(eng, i, in->buffer + local_bufs, chunk);
                 if (rc == ABG_EOVERFLOW) break;  // engine buffer full: demodulate first
                 if (rc != ABG_OK) {
                     fatal("abg_push failed");
                     abg_destroy(eng);
                     return NULL;
                 }
-                in->bufs = (in->bufs + chunk) % in->buf_size;  // not under the lock, like :669
+                // the ring space is released (bufs advanced, not under the lock, like :669) only after the copy has
+                // left the ring: with a page-locked ring abg_push is asynchronous
+                local_bufs = (local_bufs + chunk) % in->buf_size;
                 n -= chunk;
                 pushed = true;
             }
+            new_bufs[i] = local_bufs;
         }
         for (int i = 0; i < nd; i++) {  // fparms = freqlist + freq_idx, re-read before every batch (:498)
             device_t* dev = devices + d0 + i;
@@ -200,6 +219,15 @@ extern "C" void* demodulate_b200(void* params) {
             fatal("abg_run failed");
             abg_destroy(eng);
             return NULL;
+        }
+        // (after abg_run, so that waiting for the copies overlaps the kernels that were just enqueued)
+        if (pushed) {
+            if (abg_ingest_sync(eng) != ABG_OK) {
+                fatal("abg_ingest_sync failed");
+                abg_destroy(eng);
+                return NULL;
+            }
+            for (int i = 0; i < nd; i++) devices[d0 + i].input->bufs = new_bufs[i];
         }
         // ---- deliver finished batches (:621-662 + output.cpp:903-923 hand-shake) ----
         bool delivered = false;

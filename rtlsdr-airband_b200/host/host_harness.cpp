@@ -200,6 +200,8 @@ ABG_API int abh_set_freqlist(void* hp, int dev, int chan, int n_freqs, const abg
 }
 
 // feed one raw stream per device through the rings, demodulate with demodulate_b200(), consume; returns 0 on success
+static int run_with_inputs(Harness* h, std::vector<pthread_t>& fth, int timeout_s);
+
 ABG_API int abh_run(void* hp, const unsigned char* const* raws, const size_t* raw_bytes, int timeout_s) {
     Harness* h = (Harness*)hp;
     const int D = (int)h->devs.size();
@@ -209,6 +211,41 @@ ABG_API int abh_run(void* hp, const unsigned char* const* raws, const size_t* ra
         feeders[i] = {&h->inputs[i], raws[i], raw_bytes[i]};
         pthread_create(&fth[i], NULL, feeder_thread, &feeders[i]);
     }
+    return run_with_inputs(h, fth, timeout_s);
+}
+
+// the same, but every device is fed by the "pattern" input plugin (host/input_pattern.cpp) started the way input_start()
+// starts any plugin (input-common.cpp:67-83): block[i] is replayed `repeat` times, paced at speedup x real time
+// (speedup > 0, may overflow like a live SDR) or lossless (speedup == 0)
+ABG_API int abh_run_pattern(void* hp, const unsigned char* const* blocks, const size_t* block_bytes, long repeat, double speedup, int timeout_s) {
+    Harness* h = (Harness*)hp;
+    const int D = (int)h->devs.size();
+    std::vector<pthread_t> fth(D);
+    std::vector<pattern_dev_data_t> dd(D);
+    input_t* proto = pattern_input_new();  // the plugin's vtable
+    if (!proto) return -3;
+    for (int i = 0; i < D; i++) {
+        input_t& in = h->inputs[i];
+        dd[i] = {blocks[i], block_bytes[i], repeat, speedup};
+        in.dev_data = &dd[i];
+        in.init = proto->init;
+        in.run_rx_thread = proto->run_rx_thread;
+        in.set_centerfreq = proto->set_centerfreq;
+        in.stop = proto->stop;
+        if (in.init(&in) < 0) {
+            free(proto->dev_data);
+            free(proto);
+            return -3;
+        }
+    }
+    free(proto->dev_data);
+    free(proto);
+    for (int i = 0; i < D; i++) pthread_create(&fth[i], NULL, h->inputs[i].run_rx_thread, &h->inputs[i]);
+    return run_with_inputs(h, fth, timeout_s);
+}
+
+static int run_with_inputs(Harness* h, std::vector<pthread_t>& fth, int timeout_s) {
+    const int D = (int)h->devs.size();
     for (int t = 0; t < 5000; t++) {  // "wait for INPUT_RUNNING", rtl_airband.cpp:1024-1032
         bool all = true;
         for (int i = 0; i < D; i++) all = all && h->inputs[i].state != INPUT_INITIALIZED;

@@ -13,7 +13,7 @@ from .lib import LIB_DIR
 
 HOST_LIB = os.path.join(LIB_DIR, "libairband_host.so")
 HOST_SYMBOLS = ["demodulate_b200", "b200_refresh_stats", "abh_create", "abh_run", "abh_batches", "abh_waveout", "abh_iq_out", "abh_axc",
-                "abh_overflows", "abh_overruns", "abh_active_counter", "abh_last_error", "abh_destroy", "abh_set_freqlist"]
+                "abh_overflows", "abh_overruns", "abh_active_counter", "abh_last_error", "abh_destroy", "abh_set_freqlist", "abh_run_pattern", "pattern_input_new"]
 _L = None
 
 
@@ -34,14 +34,17 @@ def load():
         L.abh_active_counter.restype, L.abh_active_counter.argtypes = C.c_size_t, [vp, i, i]
         L.abh_last_error.restype, L.abh_last_error.argtypes = C.c_char_p, []
         L.abh_destroy.restype, L.abh_destroy.argtypes = None, [vp]
+        L.abh_run_pattern.restype, L.abh_run_pattern.argtypes = i, [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_long, C.c_double, i]
         L.abh_set_freqlist.restype, L.abh_set_freqlist.argtypes = i, [vp, i, i, i, vp, i]
         _L = L
     return _L
 
 
-def run_host_pipeline(cfg: Config, raws: List[np.ndarray], max_batches_per_run: int = 2, timeout_s: int = 120, freqlists=None):
+def run_host_pipeline(cfg: Config, raws: List[np.ndarray], max_batches_per_run: int = 2, timeout_s: int = 120, freqlists=None,
+                      pattern=None):
     """Feed `raws` through input rings into demodulate_b200() and collect what the output thread would see.
     `freqlists` = [(dev, chan, [Channel, ...], freq_idx)] installs scan-mode frequency lists before the thread starts.
+    `pattern` = (repeat, speedup): `raws` are blocks replayed by the "pattern" input plugin instead of being fed once.
     Returns per device (waveout[C, nb*B], iq_out[C, nb*B] complex64, axc[nb, C], info dict)."""
     L = load()
     ccfg, keep = cfg.to_c()
@@ -54,7 +57,10 @@ def run_host_pipeline(cfg: Config, raws: List[np.ndarray], max_batches_per_run: 
     raws = [np.ascontiguousarray(r) for r in raws]
     ptrs = (C.c_void_p * len(raws))(*[r.ctypes.data for r in raws])
     sizes = (C.c_size_t * len(raws))(*[r.nbytes for r in raws])
-    rc = L.abh_run(h, ptrs, sizes, timeout_s)
+    if pattern is not None:
+        rc = L.abh_run_pattern(h, ptrs, sizes, int(pattern[0]), float(pattern[1]), timeout_s)
+    else:
+        rc = L.abh_run(h, ptrs, sizes, timeout_s)
     if rc != 0:
         msg = L.abh_last_error().decode()
         L.abh_destroy(h)

@@ -358,3 +358,24 @@ def test_host_adapter_scan_channel_uses_the_selected_entry():
     assert gw.shape == ow.shape and np.array_equal(ga, oa)
     assert gate(gw, ow) <= TOL
     assert info["active"] == [int(np.sum(oa[:, 0] != ord(' ')))]
+
+
+@pytest.mark.parametrize("speedup", [0.0, 8.0], ids=["lossless", "paced_8x_realtime"])
+def test_pattern_input_plugin_through_the_adapter(speedup):
+    """The "pattern" input plugin (host/input_pattern.cpp, shape of reference src/input-file.cpp) replays a block into the
+    page-locked input rings; demodulate_b200() drains them.  Lossless mode must reproduce the oracle on block x repeat;
+    the paced mode (a live SDR never waits) must do so too as long as nothing overflowed."""
+    from airband_b200 import host
+    cfg, _ = CASES["s8_two_devices"]()
+    repeat = 3
+    blocks = [wl.synth_iq(cfg, d, 3 * cfg.wave_batch * cfg.hop(d), key_on_s=0.2, key_off_s=0.1) for d in range(2)]
+    raws = [np.tile(b, repeat) for b in blocks]
+    ores, oorc = op.run_oracle(cfg, raws)
+    hres = host.run_host_pipeline(cfg, blocks, pattern=(repeat, speedup))
+    for d in range(2):
+        gw, gi, ga, info = hres[d]
+        ow, oi, oa = ores[d]
+        assert info["overflows"] == 0 and info["overruns"] == 0, info
+        assert gw.shape == ow.shape and ow.shape[1] >= 7 * cfg.wave_batch
+        assert np.array_equal(ga, oa)
+        assert gate(gw, ow) <= TOL
