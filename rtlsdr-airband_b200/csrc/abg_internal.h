@@ -119,6 +119,7 @@ int abg_k1p_tile_frames(int fft_size, int sfmt, int hop_bytes, int max_channels,
 struct K2Launch {
     int G, Gp, P, wave_batch, fm_demod, iq_stride;  // iq_stride = nbmax * B
     int lanes_per_warp;       // channels handled by one warp of K2: 1, 2, 4, 8, 16 or 32
+    int nfm_blocks;           // some channel (or scan-list entry) is NFM: run the kernel build with the NFM steady-state blocks
     const ChanParams* params;
     ChanState* state;
     const K2Dev* devs;

@@ -273,6 +273,7 @@ struct abg_engine {
     std::vector<Device> dev;
     std::vector<Group> groups;
     std::vector<ChanParams> h_params;
+    bool any_nfm = false;  // some channel or scan-list entry demodulates NFM
     struct ScanChan {
         int g = 0, n_freqs = 0, cur = 0;
         FreqSet* stash = nullptr;  // device array [n_freqs]; entry `cur` is stale while it is live
@@ -318,6 +319,7 @@ struct abg_engine {
         K2Launch L{};
         L.G = G; L.Gp = Gp; L.P = P; L.wave_batch = B; L.fm_demod = fm_demod; L.iq_stride = nbmax * B;
         L.lanes_per_warp = k2_lpw;
+        L.nfm_blocks = any_nfm ? 1 : 0;
         L.params = params.p; L.state = state.p; L.devs = d_k2; L.bins = bins.p; L.base_bins = base_bins.p;
         L.win = win[cur].p; L.iqin = iqin[cur].p; L.win_next = win[cur ^ 1].p; L.iqin_next = iqin[cur ^ 1].p; L.wout = wout.p; L.iqout = any_iq_out ? iqout.p : nullptr;
         L.sqbuf = sqbuf.p; L.tone_coeff = tone_coeff.p; L.tone_q1 = tone_q1.p; L.tone_q2 = tone_q2.p; L.tone_mag = tone_mag.p;
@@ -539,6 +541,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         }
     }
     e->h_params = hp;
+    for (int g = 0; g < G; g++)
+        if (hp[g].modulation == ABG_MOD_NFM) e->any_nfm = true;
     e->h_bins = hb;
 
     // ---- tables -----------------------------------------------------------------------------------------------------
@@ -1090,6 +1094,7 @@ int abg_scan_configure(abg_engine* e, int dev, int chan, int n_freqs, const abg_
         std::vector<float> banks[2];
         const int rc = build_freq(e->W, freqs[i], f.p, f.s, banks, what);
         if (rc != ABG_OK) return rc;
+        if (f.p.modulation == ABG_MOD_NFM) e->any_nfm = true;
         for (int w = 0; w < 2; w++)
             for (size_t t = 0; t < banks[w].size(); t++) f.tone_coeff[w][t] = banks[w][t];
     }

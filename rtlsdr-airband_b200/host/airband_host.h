@@ -124,6 +124,7 @@ struct b200_globals {
     int fm_demod;
     volatile int do_exit;
     volatile int devices_running;
+    volatile int engine_ready;  // set by demodulate_b200() once its engine exists (load-test sources start their clock then)
     int wait_for_consumer;    // offline use (file input faster than real time): deliver a batch only once waveavail == 0
     int max_batches_per_run;
     char last_error[512];

@@ -147,6 +147,7 @@ extern "C" void* demodulate_b200(void* params) {
             scan_idx[i][c] = 0;
         }
     }
+    g_b200.engine_ready = 1;
     std::vector<float> wo, iq;
     std::vector<char> axc;
     bool idle = false;  // the previous pass neither pushed, demodulated nor delivered anything

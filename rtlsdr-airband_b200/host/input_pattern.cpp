@@ -33,8 +33,11 @@ void* pattern_rx_thread(void* ctx) {
     const size_t max_chunk = ((input->buf_size / 2 - 1) / bpc) * bpc;  // like input-file.cpp:95
     const double rate = dd->speedup > 0 ? dd->speedup * (double)input->sample_rate * (double)bpc : 0.0;  // bytes per second
     size_t sent = 0;
-    const double t0 = now_s();
     input->state = INPUT_RUNNING;
+    // paced mode: the clock starts when the demodulator is up, so that its start-up time (CUDA context, allocations) is not
+    // counted as half a second of lost samples; a real SDR is started the same way, after init_demod (rtl_airband.cpp:1024-1060)
+    while (rate > 0 && !g_b200.engine_ready && !g_b200.do_exit) usleep(1000);
+    const double t0 = now_s();
     while (!g_b200.do_exit && sent < total && input->state == INPUT_RUNNING) {
         size_t n;
         if (rate > 0) {  // live source: what the clock says is due, whether or not the consumer kept up
