@@ -158,6 +158,9 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
         for (int grp = 0; grp < NGRP; ++grp) {
             // ---- load + convert + window: GCOL columns of R1 samples ----
             float2 v[GCOL][R1];
+            // The window multiply is folded into the first radix-2 stage of the column FFT: that stage pairs sample n1 with
+            // sample n1 + R1/2 (logical A[2m], A[2m+1] live in v[m'] and v[m' + R1/2]), so with a = xa*wa the butterfly
+            // outputs are fma(xb, wb, a) and fma(-xb, wb, a): 3 instructions per real pair instead of 2 FMUL + 2 FADD.
             auto load_group = [&](auto al4_tag) {
                 constexpr bool AL4 = decltype(al4_tag)::value;
 #pragma unroll
@@ -165,18 +168,26 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                     const int j = grp * GCOL + jj;
                     const int c0 = PAIR * lane + (PAIR * 32) * (j / PAIR);     // first column of the pair
 #pragma unroll
-                    for (int n1 = 0; n1 < R1; ++n1) {
-                        const int n = c0 + M1 * n1;
+                    for (int n1 = 0; n1 < R1 / 2; ++n1) {
+                        const int na = c0 + M1 * n1, nb = c0 + M1 * (n1 + R1 / 2);
                         if constexpr (PAIR == 2) {
-                            const float2 w2 = __ldg(reinterpret_cast<const float2*>(wsc + n));
-                            float2 x0, x1;
-                            load_pair_pr<SFMT, AL4>(tile, fo + n * BPC, x0, x1);
-                            v[jj][n1] = make_float2(x0.x * w2.x, x0.y * w2.x);
-                            v[jj + 1][n1] = make_float2(x1.x * w2.y, x1.y * w2.y);
+                            const float2 wa = __ldg(reinterpret_cast<const float2*>(wsc + na));
+                            const float2 wb = __ldg(reinterpret_cast<const float2*>(wsc + nb));
+                            float2 xa0, xa1, xb0, xb1;
+                            load_pair_pr<SFMT, AL4>(tile, fo + na * BPC, xa0, xa1);
+                            load_pair_pr<SFMT, AL4>(tile, fo + nb * BPC, xb0, xb1);
+                            const float a0x = xa0.x * wa.x, a0y = xa0.y * wa.x, a1x = xa1.x * wa.y, a1y = xa1.y * wa.y;
+                            v[jj][n1] = make_float2(fmaf(xb0.x, wb.x, a0x), fmaf(xb0.y, wb.x, a0y));
+                            v[jj][n1 + R1 / 2] = make_float2(fmaf(-xb0.x, wb.x, a0x), fmaf(-xb0.y, wb.x, a0y));
+                            v[jj + 1][n1] = make_float2(fmaf(xb1.x, wb.y, a1x), fmaf(xb1.y, wb.y, a1y));
+                            v[jj + 1][n1 + R1 / 2] = make_float2(fmaf(-xb1.x, wb.y, a1x), fmaf(-xb1.y, wb.y, a1y));
                         } else {
-                            const float w = __ldg(wsc + n);
-                            const float2 x0 = load_sample_pr<SFMT>(tile, fo + n * BPC);
-                            v[jj][n1] = make_float2(x0.x * w, x0.y * w);
+                            const float wa = __ldg(wsc + na), wb = __ldg(wsc + nb);
+                            const float2 xa = load_sample_pr<SFMT>(tile, fo + na * BPC);
+                            const float2 xb = load_sample_pr<SFMT>(tile, fo + nb * BPC);
+                            const float ax = xa.x * wa, ay = xa.y * wa;
+                            v[jj][n1] = make_float2(fmaf(xb.x, wb, ax), fmaf(xb.y, wb, ay));
+                            v[jj][n1 + R1 / 2] = make_float2(fmaf(-xb.x, wb, ax), fmaf(-xb.y, wb, ay));
                         }
                     }
                 }
@@ -185,15 +196,15 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                 load_group(std::true_type{});
             else
                 load_group(std::false_type{});
-            // ---- R1-point FFT of every column (result row k in v[col][brev(k)]) ----
+            // ---- remaining stages of the R1-point FFT of every column (result row k in v[col][brev(k)]) ----
 #pragma unroll
-            for (int jj = 0; jj < GCOL; ++jj) reg_fft<R1>(v[jj]);
+            for (int jj = 0; jj < GCOL; ++jj) dit_from<R1, 4>(v[jj]);
 
             // ---- per channel: lane-partial of the dot product over this group's columns ----
 #define PR_CASE(R)                                                                   \
     case R: {                                                                        \
         _Pragma("unroll") for (int jj = 0; jj < GCOL; ++jj) {                        \
-            const float2 u = U[jj];                                                  \
+            const float2 u = uu[jj];                                                 \
             const float2 y = v[jj][brev<R1>(R)];                                     \
             sr = fmaf(y.x, u.x, sr);                                                 \
             sr = fmaf(-y.y, u.y, sr);                                                \
@@ -221,6 +232,9 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                     if (c < nch) {
                         const int row = s_k1[c];  // warp-uniform
                         const float2* U = s_U + c * NCOL + grp * GCOL;
+                        float2 uu[GCOL];
+#pragma unroll
+                        for (int jj = 0; jj < GCOL; ++jj) uu[jj] = U[jj];
                         float sr = accr[c], si = acci[c];
                         PR_ROW_SWITCH()
                         accr[c] = sr;
@@ -232,6 +246,20 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                 for (int c = 0; c < nch; ++c) {
                     const int row = s_k1[c];  // warp-uniform
                     const float2* U = s_U + c * NCOL + grp * GCOL;
+                    // the group's warp-uniform factors, fetched before the row dispatch (16-byte rows: s_U and GCOL*8 are
+                    // multiples of 16 bytes, so two columns come with one 128-bit broadcast load)
+                    float2 uu[GCOL];
+                    if constexpr (GCOL % 2 == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < GCOL; jj += 2) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(U + jj);
+                            uu[jj] = make_float2(t4.x, t4.y);
+                            uu[jj + 1] = make_float2(t4.z, t4.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < GCOL; ++jj) uu[jj] = U[jj];
+                    }
                     float sr = 0.0f, si = 0.0f;
                     PR_ROW_SWITCH()
                     // times the per-lane factor W^(PAIR*lane*b)

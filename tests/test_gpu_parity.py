@@ -379,3 +379,45 @@ def test_pattern_input_plugin_through_the_adapter(speedup):
         assert gw.shape == ow.shape and ow.shape[1] >= 7 * cfg.wave_batch
         assert np.array_equal(ga, oa)
         assert gate(gw, ow) <= TOL
+
+
+def test_full_size_cfg2_properties_and_sampled_oracle_parity():
+    """BASELINE.json configs[1] at its FULL size (64 devices x 2.56 Msps U8, fft 2048, 8 AM channels, 4 batches per run),
+    checked through properties that do not need the oracle on all 512 channels:
+      * devices that receive identical bytes produce bit-identical audio and decisions, wherever they sit in the launch
+        (tile / CTA / warp placement must not leak into results);
+      * the output-pruned and the full-spectrum K1 agree within the audio gate, with identical squelch decisions;
+      * one run of 4 batches == 4 runs of 1 batch, bit for bit;
+    plus the oracle itself on a sample of the devices (one per distinct stream)."""
+    import bench
+    cfg, _ = bench.make_workload("cfg2")
+    nb = 4
+    raws = bench.synth_streams(cfg, nb, n_unique=4)
+    D = len(cfg.devices)
+    res, eng = lib.demodulate_all(cfg, raws, max_batches_per_run=nb, fft_mode=2)
+    opened = 0
+    for d in range(D):
+        w, _, a = res[d]
+        assert w.shape == (8, nb * cfg.wave_batch)
+        w0, _, a0 = res[d % 4]
+        assert np.array_equal(w.view(np.uint32), w0.view(np.uint32)) and np.array_equal(a, a0), f"device {d} differs from its twin {d % 4}"
+        opened += int((a != ord(' ')).sum())
+    assert opened > 0
+    res_full, eng_full = lib.demodulate_all(cfg, raws, max_batches_per_run=nb, fft_mode=1)
+    res_one, eng_one = lib.demodulate_all(cfg, raws, max_batches_per_run=1, fft_mode=2)
+    for d in range(D):
+        assert np.array_equal(res[d][2], res_full[d][2])
+        assert gate(res[d][0], res_full[d][0]) <= TOL
+        assert np.array_equal(res[d][0].view(np.uint32), res_one[d][0].view(np.uint32)) and np.array_equal(res[d][2], res_one[d][2])
+    # the oracle on one device per distinct stream (channel plans are identical across devices)
+    sub = cm.Config(fft_size=cfg.fft_size, wave_rate=cfg.wave_rate, devices=cfg.devices[:4])
+    ores, oorc = op.run_oracle(sub, raws[:4])
+    for d in range(4):
+        ow, _, oa = ores[d]
+        assert np.array_equal(res[d][2], oa)
+        assert gate(res[d][0], ow) <= TOL
+        for c in range(8):
+            gs, os_ = eng.stats(d, c), oorc.stats(d, c)
+            assert gs.open_count == os_.open_count and gs.active_counter == os_.active_counter
+    for e in (eng, eng_full, eng_one):
+        e.close()
