@@ -34,7 +34,7 @@ using namespace k1;
 constexpr int PR_WARPS = 4;          // warps (= frames in flight) per CTA
 constexpr int PR_MAXCH = 32;         // channels handled per pass of the kernel
 constexpr int PR_PAD = 33;           // padded row length of the partial-sum matrix
-constexpr int PR_FEW = 8;            // up to this many channels per device: partial sums accumulate in registers
+constexpr int PR_ROWTAB = 20;        // row-start table (R1 + 1 <= 17 entries), padded to a multiple of 16 bytes
 
 
 struct PrArgs {
@@ -79,6 +79,16 @@ __device__ __forceinline__ void load_pair_pr(const unsigned char* tile, int byte
     }
 }
 
+// f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{})
+template <int... Is, class F>
+__device__ __forceinline__ void pr_static_for_impl(std::integer_sequence<int, Is...>, F& f) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void pr_static_for(F& f) {
+    pr_static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
 template <int LOGN, int SFMT, int R1, int PR_GELEM>
 __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a) {
     constexpr int N = 1 << LOGN;
@@ -95,8 +105,9 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);
     const int CM = a.nchmax;                                                         // multiple of 4
-    int* s_k1 = reinterpret_cast<int*>(smem + 16);                                   // [CM] bin mod R1
-    float2* s_U = reinterpret_cast<float2*>(smem + 16 + CM * sizeof(int));           // [CM][NCOL] warp-uniform factors
+    int* s_order = reinterpret_cast<int*>(smem + 16);                                // [CM] channels sorted by FFT row (bin mod R1)
+    int* s_rowstart = s_order + CM;                                                  // [PR_ROWTAB] first sorted position of every row
+    float2* s_U = reinterpret_cast<float2*>(smem + 16 + (CM + PR_ROWTAB) * sizeof(int));  // [CM][NCOL] warp-uniform factors
     float2* s_base = s_U + CM * NCOL;                                                // [CM][32] per-lane factors
     float* s_part = reinterpret_cast<float*>(s_base + CM * 32);                      // [PR_WARPS][2*CM][PR_PAD]
     unsigned char* tile = reinterpret_cast<unsigned char*>(s_part + PR_WARPS * 2 * CM * PR_PAD);
@@ -121,9 +132,19 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
 
     // ---- meanwhile: per-channel tables for this device ----
     const int gbase = dv.g0 + a.ch0;
-    for (int c = tid; c < nch; c += PR_WARPS * 32) {
-        const int b = a.bins[gbase + c] & (N - 1);
-        s_k1[c] = b % R1;
+    // The channel loop below walks the FFT rows in a fixed (unrolled) order and, inside a row, the channels whose bin
+    // falls on it: the row is then a compile-time register index and no per-channel dispatch is needed.  Warp 0 sorts the
+    // (<= 32) channels by row with a rank count.
+    if (tid < 32) {
+        const int myrow = (tid < nch) ? (a.bins[gbase + tid] & (N - 1)) % R1 : R1;  // R1 = "no channel"
+        int rank = 0, below = 0;
+        for (int o = 0; o < nch; ++o) {
+            const int ro = __shfl_sync(0xffffffffu, myrow, o);
+            rank += (ro < myrow || (ro == myrow && o < tid)) ? 1 : 0;
+            below += (ro < tid) ? 1 : 0;      // channels on rows < tid
+        }
+        if (tid < nch) s_order[rank] = tid;
+        if (tid <= R1) s_rowstart[tid] = below;
     }
     for (int i = tid; i < nch * NCOL; i += PR_WARPS * 32) {
         const int c = i / NCOL, j = i % NCOL;
@@ -140,9 +161,8 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
     mbar_wait0(mbar);
 
     float* part = s_part + warp * (2 * CM * PR_PAD);
-    // register-resident accumulators for <= PR_FEW channels were measured SLOWER on B200 (0.618 vs 0.541 ms on cfg2:
-    // 102 registers and a much larger unrolled body); the path is kept for reference but compiled out
-    constexpr bool few = false;
+    // (register-resident accumulators across the groups for devices with few channels were measured SLOWER on B200:
+    // 0.618 vs 0.541 ms on cfg2, 102 registers and a much larger unrolled body; partial sums go through shared memory)
     const float* __restrict__ wsc = a.wsc;
     const int iters = (nf + PR_WARPS - 1) / PR_WARPS;
     for (int it = 0; it < iters; ++it) {
@@ -150,10 +170,6 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
         if (fl >= nf) break;  // warp-uniform
         const int fo = pre + fl * dv.hop_bytes;
         const int pos = dv.pos0 + f0 + fl;
-        float accr[PR_FEW], acci[PR_FEW];
-#pragma unroll
-        for (int c = 0; c < PR_FEW; ++c) accr[c] = acci[c] = 0.0f;
-
 #pragma unroll 1
         for (int grp = 0; grp < NGRP; ++grp) {
             // ---- load + convert + window: GCOL columns of R1 samples ----
@@ -200,54 +216,16 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
 #pragma unroll
             for (int jj = 0; jj < GCOL; ++jj) dit_from<R1, 4>(v[jj]);
 
-            // ---- per channel: lane-partial of the dot product over this group's columns ----
-#define PR_CASE(R)                                                                   \
-    case R: {                                                                        \
-        _Pragma("unroll") for (int jj = 0; jj < GCOL; ++jj) {                        \
-            const float2 u = uu[jj];                                                 \
-            const float2 y = v[jj][brev<R1>(R)];                                     \
-            sr = fmaf(y.x, u.x, sr);                                                 \
-            sr = fmaf(-y.y, u.y, sr);                                                \
-            si = fmaf(y.x, u.y, si);                                                 \
-            si = fmaf(y.y, u.x, si);                                                 \
-        }                                                                            \
-    } break;
-#define PR_ROW_SWITCH()                                                                                   \
-    switch (row) {                                                                                        \
-        PR_CASE(0) PR_CASE(1) PR_CASE(2) PR_CASE(3) PR_CASE(4) PR_CASE(5) PR_CASE(6) PR_CASE(7)           \
-        default:                                                                                          \
-            if constexpr (R1 == 16) {                                                                     \
-                switch (row) {                                                                            \
-                    PR_CASE(8) PR_CASE(9) PR_CASE(10) PR_CASE(11) PR_CASE(12) PR_CASE(13) PR_CASE(14) PR_CASE(15) \
-                    default: break;                                                                       \
-                }                                                                                         \
-            }                                                                                             \
-            break;                                                                                        \
-    }
-            if (few) {
-                // up to PR_FEW channels: partial sums stay in registers across the groups (channel loop unrolled so that
-                // the accumulators are statically indexed); the per-lane factor is applied once, after the last group
-#pragma unroll
-                for (int c = 0; c < PR_FEW; ++c) {
-                    if (c < nch) {
-                        const int row = s_k1[c];  // warp-uniform
-                        const float2* U = s_U + c * NCOL + grp * GCOL;
-                        float2 uu[GCOL];
-#pragma unroll
-                        for (int jj = 0; jj < GCOL; ++jj) uu[jj] = U[jj];
-                        float sr = accr[c], si = acci[c];
-                        PR_ROW_SWITCH()
-                        accr[c] = sr;
-                        acci[c] = si;
-                    }
-                }
-            } else {
+            // ---- per FFT row, per channel on that row: lane-partial of the dot product over this group's columns ----
+            auto row_channels = [&](auto row_tag) {
+                constexpr int R = decltype(row_tag)::value;
+                const int i1 = s_rowstart[R + 1];
 #pragma unroll 1
-                for (int c = 0; c < nch; ++c) {
-                    const int row = s_k1[c];  // warp-uniform
+                for (int i = s_rowstart[R]; i < i1; ++i) {  // warp-uniform bounds
+                    const int c = s_order[i];
                     const float2* U = s_U + c * NCOL + grp * GCOL;
-                    // the group's warp-uniform factors, fetched before the row dispatch (16-byte rows: s_U and GCOL*8 are
-                    // multiples of 16 bytes, so two columns come with one 128-bit broadcast load)
+                    // the group's warp-uniform factors (16-byte rows: s_U and GCOL*8 are multiples of 16 bytes, so two
+                    // columns come with one 128-bit broadcast load)
                     float2 uu[GCOL];
                     if constexpr (GCOL % 2 == 0) {
 #pragma unroll
@@ -261,7 +239,15 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                         for (int jj = 0; jj < GCOL; ++jj) uu[jj] = U[jj];
                     }
                     float sr = 0.0f, si = 0.0f;
-                    PR_ROW_SWITCH()
+#pragma unroll
+                    for (int jj = 0; jj < GCOL; ++jj) {
+                        const float2 u = uu[jj];
+                        const float2 y = v[jj][brev<R1>(R)];
+                        sr = fmaf(y.x, u.x, sr);
+                        sr = fmaf(-y.y, u.y, sr);
+                        si = fmaf(y.x, u.y, si);
+                        si = fmaf(y.y, u.x, si);
+                    }
                     // times the per-lane factor W^(PAIR*lane*b)
                     const float2 bf = s_base[c * 32 + lane];
                     const float tr = fmaf(sr, bf.x, -si * bf.y), ti = fmaf(sr, bf.y, si * bf.x);
@@ -273,19 +259,8 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                         part[(2 * c + 1) * PR_PAD + lane] += ti;
                     }
                 }
-            }
-#undef PR_ROW_SWITCH
-#undef PR_CASE
-        }
-        if (few) {
-#pragma unroll
-            for (int c = 0; c < PR_FEW; ++c) {
-                if (c < nch) {
-                    const float2 bf = s_base[c * 32 + lane];
-                    part[(2 * c) * PR_PAD + lane] = fmaf(accr[c], bf.x, -acci[c] * bf.y);
-                    part[(2 * c + 1) * PR_PAD + lane] = fmaf(accr[c], bf.y, acci[c] * bf.x);
-                }
-            }
+            };
+            pr_static_for<R1>(row_channels);
         }
         __syncwarp();
 
@@ -321,7 +296,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
 
 size_t pr_fixed_smem(int fft_size, int r1, int cm) {
     const int ncol = fft_size / 32 / r1;
-    return 16 + cm * sizeof(int) + sizeof(float2) * (size_t)cm * ncol + sizeof(float2) * (size_t)cm * 32 + sizeof(float) * PR_WARPS * 2 * (size_t)cm * PR_PAD;
+    return 16 + (cm + PR_ROWTAB) * sizeof(int) + sizeof(float2) * (size_t)cm * ncol + sizeof(float2) * (size_t)cm * 32 + sizeof(float) * PR_WARPS * 2 * (size_t)cm * PR_PAD;
 }
 int pr_cm(int max_channels) {  // channels per pass: multiple of 4, at most PR_MAXCH
     int cm = (max_channels + 3) & ~3;
