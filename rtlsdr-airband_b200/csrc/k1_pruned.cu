@@ -248,16 +248,20 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k1_pruned_kernel(const PrArgs a
                         si = fmaf(y.x, u.y, si);
                         si = fmaf(y.y, u.x, si);
                     }
-                    // times the per-lane factor W^(PAIR*lane*b)
-                    const float2 bf = s_base[c * 32 + lane];
-                    const float tr = fmaf(sr, bf.x, -si * bf.y), ti = fmaf(sr, bf.y, si * bf.x);
-                    if (NGRP == 1 || grp == 0) {
-                        part[(2 * c) * PR_PAD + lane] = tr;
-                        part[(2 * c + 1) * PR_PAD + lane] = ti;
-                    } else {
-                        part[(2 * c) * PR_PAD + lane] += tr;
-                        part[(2 * c + 1) * PR_PAD + lane] += ti;
+                    // sums of the groups accumulate in shared memory; the per-lane factor W^(PAIR*lane*b) is the same for
+                    // every group, so it is applied once, by the last one
+                    if (NGRP > 1 && grp > 0) {
+                        sr += part[(2 * c) * PR_PAD + lane];
+                        si += part[(2 * c + 1) * PR_PAD + lane];
                     }
+                    if (grp == NGRP - 1) {
+                        const float2 bf = s_base[c * 32 + lane];
+                        const float tr = fmaf(sr, bf.x, -si * bf.y), ti = fmaf(sr, bf.y, si * bf.x);
+                        sr = tr;
+                        si = ti;
+                    }
+                    part[(2 * c) * PR_PAD + lane] = sr;
+                    part[(2 * c + 1) * PR_PAD + lane] = si;
                 }
             };
             pr_static_for<R1>(row_channels);
