@@ -92,12 +92,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout_s: float = 10.0):
+        """nvidia-smi needs a few hundred ms to produce its first row: the timed region must not start before that."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def count_between(self, t0: float, t1: float) -> int:
+        return sum(1 for (t, _) in self.rows if t0 <= t <= t1)
+
+    def stop(self, windows=None):
+        """Summary over the samples whose timestamp lies in one of `windows` [(t0, t1), ...] (None: all samples)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -105,7 +115,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for (ts, r) in self.rows:
+            if windows is not None and not any(a <= ts <= b for (a, b) in windows):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -189,7 +201,7 @@ def cpu_run(cfg, desc, steps: int, warmup: int, budget_s: float = 20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
@@ -251,24 +263,41 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     for _ in range(max(args.warmup, 1)):
         eng.run_resident(nb)
     barrier()
-    if rank == 0:
-        sampler.rows.clear()  # keep only samples taken during the timed region
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_ms, k2_ms = [], []
     barrier()
+    t_wall0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         eng.run_resident(nb)
     eng.join()  # main stream waits for the K2 stream: ev1 covers every kernel of every step
     ev1.record(stream)
     barrier()
+    t_wall1 = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        windows = [(t_wall0, t_wall1)]
+        note = None
+        if sampler.count_between(t_wall0, t_wall1) < 5:
+            # the timed region is shorter than a handful of 20 ms sampling intervals (small --steps): keep the GPU under the
+            # SAME load (identical untimed steps) until enough samples exist, and say so
+            t_x0 = time.time()
+            while sampler.proc and sampler.count_between(t_x0, time.time()) < 8 and time.time() - t_x0 < 3.0:
+                for _ in range(50):
+                    eng.run_resident(nb)
+                eng.sync()
+            windows.append((t_x0, time.time()))
+            note = "timed region shorter than 5 sampling intervals: clocks also sampled over identical untimed steps run right after it"
+        clocks = sampler.stop(windows)
+        if note:
+            clocks["note"] = note
     # per-kernel durations from the engine's own events (same stream), a few extra steps outside the timed loop
     for _ in range(5):
         eng.run_resident(nb)

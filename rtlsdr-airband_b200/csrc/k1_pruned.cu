@@ -333,12 +333,13 @@ cudaError_t pr_launch_one2(const K1Launch& L, const PrArgs& args, cudaStream_t s
 
 template <int LOGN, int SFMT, int R1>
 cudaError_t pr_launch_one(const K1Launch& L, const PrArgs& args, cudaStream_t s) {
-    // complex values held in registers per lane at once: 32 (two passes over the channels for N=2048, 88 registers, 20
-    // warps/SM) or, with ABG_K1_GELEM=64, 64 (one pass, 165 registers, 12 warps/SM)
+    // complex values held in registers per lane at once: 64 (a whole 2048-point frame in one pass over the channels, 167
+    // registers, 12 warps/SM) or, with ABG_K1_GELEM=32, 32 (two passes, 96 registers, 20 warps/SM).  Since the channel loop
+    // lost its per-channel dispatch the single pass wins (cfg2: K1 0.450 vs 0.480 ms alone, step 0.615 vs 0.655 ms).
     static int ge = 0;
     if (ge == 0) {
         const char* e = getenv("ABG_K1_GELEM");
-        ge = (e && atoi(e) == 64) ? 64 : 32;  // 32 measured best (more resident warps overlap better with K2)
+        ge = (e && atoi(e) == 32) ? 32 : 64;
     }
     if (ge == 32) return pr_launch_one2<LOGN, SFMT, R1, 32>(L, args, s);
     return pr_launch_one2<LOGN, SFMT, R1, 64>(L, args, s);
@@ -369,7 +370,7 @@ int abg_k1p_tile_frames(int fft_size, int sfmt, int hop_bytes, int max_channels,
     const int bpc = (sfmt == ABG_SFMT_U8 || sfmt == ABG_SFMT_S8) ? 2 : (sfmt == ABG_SFMT_S16 ? 4 : 8);
     const size_t fixed = pr_fixed_smem(fft_size, r1, pr_cm(max_channels));
     const size_t frame_bytes = (size_t)fft_size * bpc;
-    size_t per_cta = 40 * 1024;  // 5 CTAs (20 warps) per SM at 88 registers/thread: measured best on cfg2
+    size_t per_cta = 48 * 1024;  // 3 CTAs per SM are register-limited (167 registers/thread); 48 KB tiles measured best on cfg2
     if (const char* e = getenv("ABG_K1_CTA_KB")) per_cta = (size_t)atoi(e) * 1024;
     size_t budget = per_cta > fixed + frame_bytes + 64 ? per_cta - fixed : frame_bytes + 64;
     if (fixed + budget > 220 * 1024) return -1;
