@@ -12,7 +12,9 @@
 // 2l + 64m + {0,1}; the dot product is a per-lane partial (coefficients factor as W^(2l*b) * W^((64m+p)*b): the second
 // factor is warp-uniform and is read as a shared-memory broadcast, the first is applied once per channel) followed by
 // one shared-memory transposed reduction for all channels of the frame.  No spectrum ever leaves registers, no
-// inter-pass exchange buffer, no block-wide barrier inside the frame loop.
+// inter-pass exchange buffer, no block-wide barrier inside the frame loop.  The window multiply is folded into the first
+// radix-2 stage, and the channels are visited in FFT-row order (sorted once per CTA) so that the row a channel reads is
+// a compile-time register index.
 //
 // Frames of a tile are staged once by a TMA bulk copy exactly as in k1_fft.cu (frames overlap by N-hop samples).
 // Devices with AFC need the whole spectrum of batch-final frames (reference src/rtl_airband.cpp:180-251) and keep
