@@ -11,8 +11,11 @@ devices shard by GPU with no data-path collective, so N GPUs run N x 64 devices 
 
   value  device-timed (CUDA events on the engine's stream, max over ranks): IQ samples consumed / s, inputs resident
          in HBM (the resident stream, 168 MB per step, is larger than the 126 MB L2, so every step re-reads HBM).
-  e2e    same metric through the public C ABI with HOST buffers: abg_push (H2D) + abg_run + abg_fetch_batch (D2H)
-         inside the timed region (wall clock around synchronised steps).
+  e2e    same metric through the public C ABI with HOST buffers: abg_push (H2D from pinned memory) + abg_run +
+         abg_fetch_batches (results written by the GPU into pinned host slots, then copied to the caller's arrays) inside
+         the timed region, software-pipelined by one step like any streaming caller (wall clock around the loop).
+  clocks nvidia-smi SM clock / throttle reasons sampled every 20 ms during the timed region (the sampler's first row is
+         awaited before timing starts; a region shorter than 5 samples is extended by identical untimed steps).
   roofline     K1 (the dominant kernel): algorithmic bytes per launch / CUDA-event duration vs the measured HBM
                peak; the FP32 figures next to it are the binding ones for this path.
   cpu_baseline the CPU oracle (reference leaf classes + restated loop, the reference's own -O3 -ffast-math flags)
