@@ -421,3 +421,21 @@ def test_full_size_cfg2_properties_and_sampled_oracle_parity():
             assert gs.open_count == os_.open_count and gs.active_counter == os_.active_counter
     for e in (eng, eng_full, eng_one):
         e.close()
+
+
+@pytest.mark.parametrize("lpw", [2, 4, 32])
+@pytest.mark.parametrize("name", ["am_u8", "nfm_s16", "am_bw_f32", "s8_two_devices", "uneven_devices"])
+def test_channels_per_warp_variants_match_oracle(name, lpw, monkeypatch):
+    """K2 is compiled for 1, 2, 4, 8, 16 and 32 channels per warp and the engine picks by channel count (more than 592
+    channels -> several per warp), which the small cases never reach: force the wide variants.  `uneven_devices` feeds
+    the two devices of one warp different numbers of batches, so some runs advance only one of them."""
+    monkeypatch.setenv("ABG_K2_LPW", str(lpw))
+    if name == "uneven_devices":
+        cfg, _ = CASES["s8_two_devices"]()
+        raws = [wl.synth_iq(cfg, i, wl.samples_for_batches(cfg, i, nb), key_on_s=0.1, key_off_s=0.05) for i, nb in enumerate((2, 5))]
+    else:
+        cfg, raws = CASES[name]()
+    ores, oorc = op.run_oracle(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws, max_batches_per_run=2)
+    compare(cfg, raws, gres, geng, ores, oorc)
+    geng.close()
