@@ -186,6 +186,9 @@ class Oracle:
         assert self.L.abo_get_stats(self.h, dev, chan, C.byref(s)) == 0
         return s
 
+    def set_bin(self, dev: int, chan: int, bin_: int) -> None:
+        assert self.L.abo_set_bin(self.h, dev, chan, bin_) == 0
+
     def scan_configure(self, dev: int, chan: int, freqs) -> None:
         """Install a scan-mode frequency list (list of config.Channel); entry 0 becomes current."""
         from airband_b200.config import channels_to_c

@@ -439,3 +439,30 @@ def test_channels_per_warp_variants_match_oracle(name, lpw, monkeypatch):
     gres, geng = lib.demodulate_all(cfg, raws, max_batches_per_run=2)
     compare(cfg, raws, gres, geng, ores, oorc)
     geng.close()
+
+
+def test_set_bin_moves_a_channel_between_runs():
+    """abg_set_bin (what a retune does to dev->bins[] / base_bins[]): channel 0 is moved onto channel 1's bin after two
+    batches and back after four; the oracle gets the same calls at the same batch boundaries."""
+    cfg, _ = CASES["am_u8"]()
+    nb_total = 6
+    raw = wl.synth_iq(cfg, 0, wl.samples_for_batches(cfg, 0, nb_total), key_on_s=0.11, key_off_s=0.07, amplitude=0.2)
+    b0, b1 = cfg.devices[0].channels[0].bin, cfg.devices[0].channels[1].bin
+    o = op.Oracle(cfg)
+    e = lib.Engine(cfg, max_batches_per_run=2, input_capacity_batches=5)
+    pos = 0
+    for k, new_bin in enumerate((None, b1, b0)):
+        need = wl.samples_for_batches(cfg, 0, 2 * (k + 1)) * 2
+        if new_bin is not None:
+            o.set_bin(0, 0, new_bin)
+            e.set_bin(0, 0, new_bin)
+        o.push(0, raw[pos:need]); e.push(0, raw[pos:need])
+        pos = need
+        assert o.run(2) == 2 and e.run(2) == 2
+        ow, _, oa = o.fetch_all(0)
+        outs = [e.fetch(0) for _ in range(2)]
+        gw = np.concatenate([x[0] for x in outs], 1)
+        assert np.array_equal(np.stack([x[2] for x in outs]), oa), k
+        assert gate(gw, ow) <= TOL, (k, gate(gw, ow))
+        assert e.stats(0, 0).bin == o.stats(0, 0).bin == (new_bin if new_bin is not None else b0)
+    e.close(); o.close()
