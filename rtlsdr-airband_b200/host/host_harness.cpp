@@ -283,6 +283,74 @@ static int run_with_inputs(Harness* h, std::vector<pthread_t>& fth, int timeout_
     return timed_out ? -1 : 0;
 }
 
+// CPU-only self-test of the ingest side (no engine involved): the "pattern" plugin fills an input ring through
+// circbuffer_append() while a consumer drains it the way demodulate() does (available bytes under buffer_lock, bufs
+// advanced without it) and checks every byte against the replayed block.
+// consumer_delay_us > 0 makes the consumer slower than a paced source so that the ring overflows (overflow_count).
+// Returns the number of mismatching bytes (-1: set-up failure); *consumed / *overflows report what happened.
+ABG_API long abh_pattern_selftest(int sfmt, int sample_rate, size_t fft_size, const unsigned char* block, size_t block_len, long repeat,
+                                  double speedup, int consumer_delay_us, size_t* consumed, size_t* overflows) {
+    memset(&g_b200, 0, sizeof(g_b200));
+    g_b200.fft_size = fft_size;
+    g_b200.engine_ready = 1;
+    input_t* in = pattern_input_new();
+    if (!in) return -1;
+    in->sfmt = (sample_format_t)sfmt;
+    in->bytes_per_sample = sfmt == ABG_SFMT_S16 ? 2 : (sfmt == ABG_SFMT_F32 ? 4 : 1);
+    in->sample_rate = sample_rate;
+    pattern_dev_data_t* dd = (pattern_dev_data_t*)in->dev_data;
+    *dd = {block, block_len, repeat, speedup};
+    const size_t bpc = 2 * (size_t)in->bytes_per_sample, tail = bpc * fft_size;
+    in->buf_size = 256 * 1024;  // a small ring so that it wraps many times
+    in->buf_size -= in->buf_size % bpc;
+    std::vector<unsigned char> ring(in->buf_size + tail, 0);
+    in->buffer = ring.data();
+    pthread_mutex_init(&in->buffer_lock, NULL);
+    in->state = INPUT_INITIALIZED;
+    if (in->init(in) < 0) {
+        free(in->dev_data);
+        free(in);
+        return -1;
+    }
+    pthread_create(&in->rx_thread, NULL, in->run_rx_thread, in);
+    long bad = 0;
+    size_t pos = 0;
+    const size_t total = block_len * (size_t)repeat;
+    int idle_ms = 0;
+    while (idle_ms < 2000) {
+        size_t available;
+        pthread_mutex_lock(&in->buffer_lock);
+        available = in->bufe >= in->bufs ? in->bufe - in->bufs : in->buf_size - in->bufs + in->bufe;
+        pthread_mutex_unlock(&in->buffer_lock);
+        if (available == 0) {
+            if (in->state != INPUT_RUNNING && in->state != INPUT_INITIALIZED) break;  // source finished and ring drained
+            usleep(1000);
+            idle_ms++;
+            continue;
+        }
+        idle_ms = 0;
+        if (in->overflow_count == 0) {  // after an overflow the byte positions no longer line up: only count from then on
+            for (size_t k = 0; k < available; k++) {
+                const unsigned char got = in->buffer[(in->bufs + k) % in->buf_size];
+                if (got != block[(pos + k) % block_len]) bad++;
+            }
+        }
+        pos += available;
+        in->bufs = (in->bufs + available) % in->buf_size;  // not under the lock, like rtl_airband.cpp:669
+        if (consumer_delay_us > 0) usleep(consumer_delay_us);
+    }
+    g_b200.do_exit = 1;
+    pthread_join(in->rx_thread, NULL);
+    if (consumed) *consumed = pos;
+    if (overflows) *overflows = in->overflow_count;
+    if (in->overflow_count == 0 && pos != total) bad += 1000000;
+    pthread_mutex_destroy(&in->buffer_lock);
+    free(in->dev_data);
+    free(in);
+    g_b200.do_exit = 0;
+    return bad;
+}
+
 ABG_API int abh_batches(void* hp, int dev) { return ((Harness*)hp)->n_batches[dev]; }
 ABG_API const float* abh_waveout(void* hp, int dev) { return ((Harness*)hp)->out_wave[dev].data(); }
 ABG_API const float* abh_iq_out(void* hp, int dev) { return ((Harness*)hp)->out_iq[dev].data(); }

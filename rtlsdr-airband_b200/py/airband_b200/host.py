@@ -13,7 +13,7 @@ from .lib import LIB_DIR
 
 HOST_LIB = os.path.join(LIB_DIR, "libairband_host.so")
 HOST_SYMBOLS = ["demodulate_b200", "b200_refresh_stats", "abh_create", "abh_run", "abh_batches", "abh_waveout", "abh_iq_out", "abh_axc",
-                "abh_overflows", "abh_overruns", "abh_active_counter", "abh_last_error", "abh_destroy", "abh_set_freqlist", "abh_run_pattern", "pattern_input_new"]
+                "abh_overflows", "abh_overruns", "abh_active_counter", "abh_last_error", "abh_destroy", "abh_set_freqlist", "abh_run_pattern", "pattern_input_new", "abh_pattern_selftest"]
 _L = None
 
 
@@ -35,6 +35,8 @@ def load():
         L.abh_last_error.restype, L.abh_last_error.argtypes = C.c_char_p, []
         L.abh_destroy.restype, L.abh_destroy.argtypes = None, [vp]
         L.abh_run_pattern.restype, L.abh_run_pattern.argtypes = i, [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_long, C.c_double, i]
+        L.abh_pattern_selftest.restype = C.c_long
+        L.abh_pattern_selftest.argtypes = [i, i, C.c_size_t, vp, C.c_size_t, C.c_long, C.c_double, i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.abh_set_freqlist.restype, L.abh_set_freqlist.argtypes = i, [vp, i, i, i, vp, i]
         _L = L
     return _L
@@ -78,3 +80,13 @@ def run_host_pipeline(cfg: Config, raws: List[np.ndarray], max_batches_per_run: 
         out.append((wo.transpose(1, 0, 2).reshape(Cn, nb * B), iq.transpose(1, 0, 2).reshape(Cn, nb * 2 * B).view(np.complex64), ax, info))
     L.abh_destroy(h)
     return out
+
+
+def pattern_selftest(block: np.ndarray, sfmt: int, sample_rate: int, fft_size: int, repeat: int, speedup: float, consumer_delay_us: int = 0):
+    """CPU-only: the "pattern" input plugin into a ring drained by a checking consumer.  Returns (mismatches, bytes consumed, overflows)."""
+    L = load()
+    block = np.ascontiguousarray(block)
+    consumed, overflows = C.c_size_t(0), C.c_size_t(0)
+    bad = L.abh_pattern_selftest(sfmt, sample_rate, fft_size, block.ctypes.data, block.nbytes, repeat, float(speedup), consumer_delay_us,
+                                 C.byref(consumed), C.byref(overflows))
+    return int(bad), int(consumed.value), int(overflows.value)
