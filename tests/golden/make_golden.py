@@ -21,7 +21,7 @@ for p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), os.path.joi
 import oracle_py as op  # noqa: E402
 from cases import CASES  # noqa: E402
 
-GOLDEN = ["am_u8", "nfm_s16", "am_bw_f32"]
+GOLDEN = ["am_u8", "nfm_s16", "am_bw_f32", "s8_two_devices"]
 
 
 def main():

@@ -10,7 +10,7 @@ import oracle_py as op
 from cases import CASES
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-NAMES = ["am_u8", "nfm_s16", "am_bw_f32"]
+NAMES = ["am_u8", "nfm_s16", "am_bw_f32", "s8_two_devices"]
 
 
 def load(name):

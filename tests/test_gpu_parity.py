@@ -49,7 +49,7 @@ def test_case_matches_oracle(name, fft_mode):
     compare(cfg, raws, gres, geng, ores, oorc)
 
 
-@pytest.mark.parametrize("name", ["am_u8", "nfm_s16", "am_bw_f32"])
+@pytest.mark.parametrize("name", ["am_u8", "nfm_s16", "am_bw_f32", "s8_two_devices"])
 def test_case_matches_golden_fixture(name):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
     cfg, _ = CASES[name]()
