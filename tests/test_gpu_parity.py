@@ -466,3 +466,18 @@ def test_set_bin_moves_a_channel_between_runs():
         assert gate(gw, ow) <= TOL, (k, gate(gw, ow))
         assert e.stats(0, 0).bin == o.stats(0, 0).bin == (new_bin if new_bin is not None else b0)
     e.close(); o.close()
+
+
+@pytest.mark.parametrize("name,fill", [("am_u8", 127), ("am_u8", 0), ("am_bw_f32", 0.0), ("nfm_s16", 0)],
+                         ids=["u8_midscale", "u8_rail", "f32_zeros", "s16_zeros"])
+def test_constant_input_edge_cases(name, fill):
+    """Silence and a railed ADC: every frame identical, exact zeros through sqrt / divisions / the squelch estimators
+    (F32 and S16 zeros give |X| == 0 everywhere).  Outputs must stay finite and equal the oracle's."""
+    cfg, raws = CASES[name]()
+    raws = [np.full_like(r, fill) for r in raws]
+    ores, oorc = op.run_oracle(cfg, raws)
+    gres, geng = lib.demodulate_all(cfg, raws)
+    for d in range(len(raws)):
+        assert np.isfinite(gres[d][0]).all()
+    compare(cfg, raws, gres, geng, ores, oorc)
+    geng.close()
