@@ -99,7 +99,9 @@ typedef struct abg_options {
     int32_t cuda_device;        /* ordinal; -1 = current device */
     int32_t max_batches_per_run;/* capacity of one abg_run() per device, in WAVE_BATCH units (default 4) */
     int32_t input_capacity_batches; /* device-side raw sample buffer per device, in batches of input (default max_batches_per_run + 2) */
-    int32_t fft_mode;           /* 0 auto, 1 full spectrum every frame, 2 output-pruned last pass (only the configured bins) */
+    int32_t fft_mode;           /* 0 auto, 1 full spectrum every frame, 2 output-pruned last pass (only the configured bins, FP32 pipes),
+                                   3 the configured bins' DFT as an integer GEMM on the tensor cores (U8/S8 input whose hop is a
+                                   multiple of 16 samples; other devices use 2) */
     int32_t reserved[4];
 } abg_options;
 
@@ -151,6 +153,9 @@ ABG_API int abg_get_stats(abg_engine* e, int dev, int chan, abg_squelch_stats* o
 /* Retune a channel's bin between batches: scan mode (controller_thread, reference src/rtl_airband.cpp:101-139) or an
  * external AFC.  Sets both bins[] and base_bins[]. */
 ABG_API int abg_set_bin(abg_engine* e, int dev, int chan, int bin);
+
+/* Which K1 implementation a device's frames go through: 1 full-spectrum FFT, 2 output-pruned FFT, 3 tensor-core DFT. */
+ABG_API int abg_fft_path(const abg_engine* e, int dev);
 
 /* ---- benchmark / multi-GPU helpers (not part of the reference surface) -------------------------------------- */
 /* Upload a raw stream that stays resident in HBM and is replayed by abg_run_resident(): the timed region of the
@@ -217,6 +222,11 @@ ABG_API int abg_mixer_device_buffers(abg_engine* e, float** dev_sums, int32_t** 
 /* Run conversion + window + FFT on one frame of `dev`'s format and return the full spectrum in natural bin order
  * (fftout[2*fft_size]); exercises the same kernel code as abg_run. */
 ABG_API int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout);
+/* Host-only: plan and coefficient table of the tensor-core K1 (fft_mode 3) for one device, as abg_create builds them
+ * (window * twiddle quantised to `digits` signed 8-bit digits, in the shared-memory image the MMA reads).
+ * plan[12] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo}; tab == NULL queries the plan only. */
+ABG_API int abg_debug_tc_table(int fft_size, int sfmt, int hop_bytes, float fullscale, int n_channels, const int32_t* bins, int digits,
+                               int32_t* plan, signed char* tab, size_t tab_cap, long long* sq, double* cscale);
 
 #ifdef __cplusplus
 }

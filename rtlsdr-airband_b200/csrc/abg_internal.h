@@ -15,6 +15,29 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
+// Kernel function attributes (dynamic shared-memory opt-in, carveout) are per CUDA device: several engines may live on
+// different GPUs of one process and several demod threads may launch concurrently.  One slot per device ordinal keeps the
+// largest size configured so far for a kernel instantiation; `apply` runs (under the lock) only when it has to grow.
+struct AbgPerDeviceSize {
+    std::mutex m;
+    size_t v[64] = {};
+    template <class F>
+    cudaError_t ensure(size_t want, F&& apply) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        std::lock_guard<std::mutex> lock(m);
+        if (want > v[dev]) {
+            cudaError_t e = apply();
+            if (e != cudaSuccess) return e;
+            v[dev] = want;
+        }
+        return cudaSuccess;
+    }
+};
+
 #define ABG_AGC_EXTRA 100     // reference src/rtl_airband.h:74
 #define ABG_SQ_BUF 102        // Squelch::buffer_size_, reference src/squelch.cpp:67
 #define ABG_MAX_TONES 52      // wanted tone + 51 standard tones, reference src/ctcss.cpp:89-111
@@ -115,6 +138,25 @@ int abg_k1_tile_frames(int fft_size, int sfmt, int hop_bytes, int* tile_bytes_ca
 // output-pruned variant (k1_pruned.cu): only the configured bins are evaluated in the last pass
 cudaError_t abg_launch_k1_pruned(const K1Launch& L, const float2* twn, int max_channels, cudaStream_t s);
 int abg_k1p_tile_frames(int fft_size, int sfmt, int hop_bytes, int max_channels, int* tile_bytes_cap);
+
+// tensor-core variant (k1_tc.cu): the bins' DFT as an integer GEMM on tcgen05 (8-bit formats, hop_bytes % 32 == 0)
+struct K1TcPlan {
+    int eligible;
+    int K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo;
+    size_t table_bytes;
+};
+struct K1TcTables {
+    const int32_t* tab_of_dev;  // [n_devices of the group] coefficient table of each device
+    const signed char* btab;    // [n_tables][K * NC]
+    const long long* sq;        // [n_tables][C2p]
+    int* counter;               // tile queue head, zero at launch
+    int32_t* status;            // != 0 after a pipeline stall inside the kernel (bounded waits, never hangs)
+    double cscale;
+};
+int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int digits, K1TcPlan* p);
+void abg_k1tc_build_table(const K1TcPlan& p, int fft_size, int sfmt, const float* wsc, const int32_t* bins, int n_channels, signed char* tab,
+                          long long* sq, double* cscale);
+cudaError_t abg_launch_k1_tc(const K1Launch& L, const K1TcPlan& p, const K1TcTables& T, int sm_count, cudaStream_t s);
 
 struct K2Launch {
     int G, Gp, P, wave_batch, fm_demod, iq_stride;  // iq_stride = nbmax * B

@@ -249,8 +249,17 @@ struct Group {
     int max_channels = 0;
     bool pruned = false;                               // which kernel this group runs
     DevBuf<float> wsc;
-    K1Dev* d_k1 = nullptr;  // device array [devs.size()]
+    std::vector<float> h_wsc;
+    K1Dev* d_k1 = nullptr;  // device array [devs.size() + 1]: the extra (all-zero) entry is the tensor-core kernel's tile counter
     std::vector<K1Dev> h_k1;  // host copy, uploaded by value with every run (upload_small)
+    // tensor-core K1 (k1_tc.cu)
+    bool use_tc = false;
+    K1TcPlan tc{};
+    DevBuf<signed char> tc_btab;
+    DevBuf<long long> tc_sq;
+    DevBuf<int32_t> tc_tab_of_dev;
+    double tc_cscale = 0.0;
+    int tc_tables = 0;
 };
 
 struct Slot {
@@ -268,7 +277,10 @@ struct Slot {
 
 struct abg_engine {
     int N = 0, W = 0, B = 0, fm_demod = 0, nbmax = 4, P = 0, G = 0, Gp = 0, fft_mode = 0;
-    int cuda_dev = 0;
+    int cuda_dev = 0, sm_count = 148, tc_digits = 4;
+    bool tc_auto = false;              // fft_mode 0 picks the tensor-core K1 for eligible groups
+    int32_t* tc_status = nullptr;      // pinned + mapped: the tensor-core K1 reports a stalled pipeline here (never hangs)
+    int32_t* tc_status_dev = nullptr;
     bool any_iq_out = false;
     std::vector<Device> dev;
     std::vector<Group> groups;
@@ -343,8 +355,10 @@ void engine_free(abg_engine* e) {
     }
     for (auto& g : e->groups) {
         g.wsc.free();
+        g.tc_btab.free(); g.tc_sq.free(); g.tc_tab_of_dev.free();
         if (g.d_k1) cudaFree(g.d_k1);
     }
+    if (e->tc_status) cudaFreeHost(e->tc_status);
     e->params.free(); e->state.free(); e->bins.free(); e->base_bins.free(); e->win[0].free(); e->win[1].free(); e->wout.free(); e->sqbuf.free();
     e->tone_coeff.free(); e->tone_q1.free(); e->tone_q2.free(); e->tone_mag.free(); e->lut.free(); e->iqin[0].free(); e->iqin[1].free(); e->iqout.free();
     e->tw1.free(); e->tw2.free(); e->twn.free(); e->axc.free(); e->mix_sums.free(); e->mix_flags.free(); e->mix_offsets.free(); e->mix_inputs.free();
@@ -455,6 +469,55 @@ int build_freq(int W, const abg_channel_cfg& cc, ChanParams& p, ChanState& s, st
     return ABG_OK;
 }
 
+// 7-term Blackman-Harris window: float literals held in double, evaluated in double, stored float (rtl_airband.cpp:335-351)
+std::vector<float> make_window(int N) {
+    std::vector<float> window(N);
+    const double a0 = 0.27105140069342f, a1 = 0.43329793923448f, a2 = 0.21812299954311f, a3 = 0.06592544638803f;
+    const double a4 = 0.01081174209837f, a5 = 0.00077658482522f, a6 = 0.00001388721735f;
+    const size_t fft_size = N;
+    for (size_t i = 0; i < fft_size; i++) {
+        double x = a0 - (a1 * cos((2.0 * M_PI * i) / (fft_size - 1))) + (a2 * cos((4.0 * M_PI * i) / (fft_size - 1))) - (a3 * cos((6.0 * M_PI * i) / (fft_size - 1))) +
+                   (a4 * cos((8.0 * M_PI * i) / (fft_size - 1))) - (a5 * cos((10.0 * M_PI * i) / (fft_size - 1))) + (a6 * cos((12.0 * M_PI * i) / (fft_size - 1)));
+        window[i] = (float)x;
+    }
+    return window;
+}
+float sample_scale(int sfmt, float fullscale) {
+    // U8 levels are (i-127.5)/127.5, S8 i/128 (rtl_airband.cpp:319-324); S16/F32 scale = 1/fullscale (:403,421)
+    return sfmt == ABG_SFMT_U8 ? 1.0f / 127.5f : sfmt == ABG_SFMT_S8 ? 1.0f / 128.0f : 1.0f / fullscale;
+}
+
+// (Re)build the tensor-core K1's coefficient tables of one launch group from the host copy of bins[]: one table per
+// distinct list of bins (synthetic many-device configs share one), tab_of_dev[] maps the group's devices to tables.
+int rebuild_tc_tables(abg_engine* e, Group& g) {
+    std::vector<std::vector<int32_t>> keys;
+    std::vector<int32_t> tab_of_dev(g.devs.size());
+    for (size_t k = 0; k < g.devs.size(); k++) {
+        const Device& d = e->dev[g.devs[k]];
+        std::vector<int32_t> key(e->h_bins.begin() + d.g0, e->h_bins.begin() + d.g0 + d.C);
+        size_t t = 0;
+        while (t < keys.size() && keys[t] != key) t++;
+        if (t == keys.size()) keys.push_back(key);
+        tab_of_dev[k] = (int32_t)t;
+    }
+    const size_t nt = keys.size();
+    std::vector<signed char> tab(nt * g.tc.table_bytes);
+    std::vector<long long> sq(nt * g.tc.C2p);
+    for (size_t t = 0; t < nt; t++)
+        abg_k1tc_build_table(g.tc, e->N, g.sfmt, g.h_wsc.data(), keys[t].data(), (int)keys[t].size(), tab.data() + t * g.tc.table_bytes,
+                             sq.data() + t * g.tc.C2p, &g.tc_cscale);
+    if ((int)nt != g.tc_tables) {
+        g.tc_btab.free(); g.tc_sq.free();
+        if (g.tc_btab.alloc(tab.size()) || g.tc_sq.alloc(sq.size())) return fail(ABG_ENOMEM, "Out of device memory for the tensor-core coefficient tables");
+        g.tc_tables = (int)nt;
+    }
+    if (!g.tc_tab_of_dev.p && g.tc_tab_of_dev.alloc(tab_of_dev.size())) return fail(ABG_ENOMEM, "Out of device memory for the tensor-core coefficient tables");
+    CU(cudaMemcpy(g.tc_btab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g.tc_sq.p, sq.data(), sizeof(long long) * sq.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g.tc_tab_of_dev.p, tab_of_dev.data(), sizeof(int32_t) * tab_of_dev.size(), cudaMemcpyHostToDevice));
+    return ABG_OK;
+}
+
 int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     Plan plan;
     if (!plan_for(cfg->fft_size, &plan)) return fail(ABG_EINVAL, "fft_size=%d not supported. Try a power of two between 256 and 8192.", cfg->fft_size);
@@ -467,6 +530,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     e->fm_demod = cfg->fm_demod;
     e->nbmax = (opt && opt->max_batches_per_run > 0) ? opt->max_batches_per_run : 4;
     e->fft_mode = opt ? opt->fft_mode : 0;
+    if (const char* ev = getenv("ABG_K1_TC_DIGITS")) e->tc_digits = atoi(ev) == 3 ? 3 : 4;
+    if (const char* ev = getenv("ABG_K1_TC_AUTO")) e->tc_auto = atoi(ev) != 0;
     const int in_cap_batches = (opt && opt->input_capacity_batches > 0) ? opt->input_capacity_batches : e->nbmax + 2;
     e->P = ABG_AGC_EXTRA + e->nbmax * e->B;
     const int N = e->N, B = e->B;
@@ -546,17 +611,7 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     e->h_bins = hb;
 
     // ---- tables -----------------------------------------------------------------------------------------------------
-    std::vector<float> window(N);
-    {  // rtl_airband.cpp:335-351
-        const double a0 = 0.27105140069342f, a1 = 0.43329793923448f, a2 = 0.21812299954311f, a3 = 0.06592544638803f;
-        const double a4 = 0.01081174209837f, a5 = 0.00077658482522f, a6 = 0.00001388721735f;
-        const size_t fft_size = N;
-        for (size_t i = 0; i < fft_size; i++) {
-            double x = a0 - (a1 * cos((2.0 * M_PI * i) / (fft_size - 1))) + (a2 * cos((4.0 * M_PI * i) / (fft_size - 1))) - (a3 * cos((6.0 * M_PI * i) / (fft_size - 1))) +
-                       (a4 * cos((8.0 * M_PI * i) / (fft_size - 1))) - (a5 * cos((10.0 * M_PI * i) / (fft_size - 1))) + (a6 * cos((12.0 * M_PI * i) / (fft_size - 1)));
-            window[i] = (float)x;
-        }
-    }
+    const std::vector<float> window = make_window(N);
     std::vector<float> h_lut(2 * 257);
     for (uint32_t i = 0; i < 256; i++) sincosf(2.0F * M_PI * (float)i / 256.0f, &h_lut[i], &h_lut[257 + i]);  // util.cpp:105-110
     h_lut[256] = h_lut[0];
@@ -608,6 +663,9 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     // ---- CUDA resources ----------------------------------------------------------------------------------------------------
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
+    CU(cudaHostAlloc((void**)&e->tc_status, 64, cudaHostAllocMapped));
+    memset(e->tc_status, 0, 64);
+    CU(cudaHostGetDevicePointer((void**)&e->tc_status_dev, e->tc_status, 0));
     {
         // K2's few long-running warps must get their SM slots ahead of the next run's K1 blocks
         int lo = 0, hi = 0;
@@ -645,16 +703,23 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
             if (e->dev[di].has_afc) group_afc = true;
         }
         g.p_frames_per_tile = abg_k1p_tile_frames(N, g.sfmt, g.hop_bytes, g.max_channels, &g.p_tile_bytes_cap);
-        // fft_mode: 0 auto = output-pruned last pass unless the group needs whole spectra (AFC); 1 = always full; 2 = pruned
+        // fft_mode: 0 auto; 1 = full spectrum every frame; 2 = output-pruned last pass on the FP32 pipes; 3 = the bins' DFT as an
+        // integer GEMM on the tensor cores (8-bit formats; other groups fall back to 2).  Groups with AFC need whole spectra.
         g.pruned = (e->fft_mode != 1) && !group_afc && g.p_frames_per_tile >= 1;
-        // window * 1/full-scale: U8 levels are (i-127.5)/127.5, S8 i/128 (rtl_airband.cpp:319-324); S16/F32 scale = 1/fullscale (:403,421)
-        float scale = g.sfmt == ABG_SFMT_U8 ? 1.0f / 127.5f : g.sfmt == ABG_SFMT_S8 ? 1.0f / 128.0f : 1.0f / g.fullscale;
+        const bool want_tc = e->fft_mode == 3 || (e->fft_mode == 0 && e->tc_auto);
+        g.use_tc = want_tc && !group_afc && abg_k1tc_plan(N, g.sfmt, g.hop_bytes, g.max_channels, e->tc_digits, &g.tc) == 1;
+        const float scale = sample_scale(g.sfmt, g.fullscale);  // window * 1/full-scale
         std::vector<float> wsc(N);
         for (int i = 0; i < N; i++) wsc[i] = window[i] * scale;
+        g.h_wsc = wsc;
         CU(g.wsc.alloc(N));
         CU(cudaMemcpy(g.wsc.p, wsc.data(), N * sizeof(float), cudaMemcpyHostToDevice));
-        CU(cudaMalloc((void**)&g.d_k1, sizeof(K1Dev) * g.devs.size() + 16));
-        g.h_k1.assign(g.devs.size(), K1Dev{});
+        CU(cudaMalloc((void**)&g.d_k1, sizeof(K1Dev) * (g.devs.size() + 1)));
+        g.h_k1.assign(g.devs.size() + 1, K1Dev{});
+        if (g.use_tc) {
+            const int rc = rebuild_tc_tables(e, g);
+            if (rc != ABG_OK) return rc;
+        }
     }
     for (auto& d : e->dev) {
         // room for in_cap_batches batches + the AGC_EXTRA priming frames + one window, + slack for 16-byte TMA rounding
@@ -768,7 +833,8 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         }
         if (max_frames == 0) continue;
         {
-            const int nl = upload_small(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * g.devs.size(), sa);
+            // (the trailing all-zero entry resets the tensor-core kernel's tile counter)
+            const int nl = upload_small(g.d_k1, g.h_k1.data(), sizeof(K1Dev) * (g.devs.size() + (g.use_tc ? 1 : 0)), sa);
             if (nl < 0) return fail(ABG_ECUDA, "K1 parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             e->launches += (uint64_t)nl;
         }
@@ -778,9 +844,18 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
         L.tile_bytes_cap = g.pruned ? g.p_tile_bytes_cap : g.tile_bytes_cap;
         L.devs = g.d_k1; L.bins = e->bins.p; L.window_scaled = g.wsc.p; L.tw1 = e->tw1.p;
         L.tw2 = e->tw2.p; L.win = e->win[cur].p; L.iqin = e->iqin[cur].p; L.Gp = e->Gp; L.sfmt = g.sfmt;
-        cudaError_t er1 = g.pruned ? abg_launch_k1_pruned(L, e->twn.p, g.max_channels, sa) : abg_launch_k1(L, sa);
+        cudaError_t er1;
+        if (g.use_tc) {
+            K1TcTables T{};
+            T.tab_of_dev = g.tc_tab_of_dev.p; T.btab = g.tc_btab.p; T.sq = g.tc_sq.p;
+            T.counter = reinterpret_cast<int*>(g.d_k1 + g.devs.size());
+            T.status = e->tc_status_dev; T.cscale = g.tc_cscale;
+            er1 = abg_launch_k1_tc(L, g.tc, T, e->sm_count, sa);
+        } else {
+            er1 = g.pruned ? abg_launch_k1_pruned(L, e->twn.p, g.max_channels, sa) : abg_launch_k1(L, sa);
+        }
         if (er1 != cudaSuccess) return fail(ABG_ECUDA, "K1 launch failed: %s", cudaGetErrorString(er1));
-        e->launches += g.pruned ? (uint64_t)((g.max_channels + 31) / 32) : 1;
+        e->launches += g.use_tc ? 1 : g.pruned ? (uint64_t)((g.max_channels + 31) / 32) : 1;
     }
     CU(cudaEventRecord(tl[1], sa));
     CU(cudaEventRecord(e->ev_k1[cur], sa));
@@ -894,6 +969,7 @@ int abg_create(const abg_config* cfg, const abg_options* opt, abg_engine** out) 
         delete e;
         return fail(ABG_ENODEV, "CUDA device has compute capability %d.x; this library contains sm_100a code only", major);
     }
+    e->sm_count = prop.multiProcessorCount;
     int rc = build(e, cfg, opt);
     if (rc != ABG_OK) {
         std::string keep = g_err;
@@ -968,6 +1044,7 @@ int abg_sync(abg_engine* e) {
     CU(cudaStreamSynchronize(e->stream_c));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaStreamSynchronize(e->stream_b));
+    if (e->tc_status && e->tc_status[0]) return fail(ABG_ECUDA, "tensor-core K1 pipeline stalled (wait code %d); results of that run are invalid", e->tc_status[0]);
     return ABG_OK;
 }
 
@@ -990,6 +1067,7 @@ int abg_fetch_batch(abg_engine* e, int dev, float* waveout, float* iq_out, char*
     Slot& s = e->slots[r.first];
     cudaSetDevice(e->cuda_dev);
     CU(cudaEventSynchronize(s.done));
+    if (e->tc_status && e->tc_status[0]) return fail(ABG_ECUDA, "tensor-core K1 pipeline stalled (wait code %d); results of that run are invalid", e->tc_status[0]);
     const int B = e->B;
     const size_t stride = (size_t)e->nbmax * B;
     for (int c = 0; c < d.C; c++) {
@@ -1065,7 +1143,16 @@ int abg_set_bin(abg_engine* e, int dev, int chan, int bin) {
     CU(cudaMemcpyAsync(e->bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->base_bins.p + d.g0 + chan, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    e->h_bins[d.g0 + chan] = bin;
+    Group& g = e->groups[d.group];
+    if (g.use_tc) return rebuild_tc_tables(e, g);  // the coefficient table carries the bin
     return ABG_OK;
+}
+
+int abg_fft_path(const abg_engine* e, int dev) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return ABG_ERANGE;
+    const Group& g = e->groups[e->dev[dev].group];
+    return g.use_tc ? 3 : (g.pruned ? 2 : 1);
 }
 
 // ---- scan mode -------------------------------------------------------------------------------------------------------
@@ -1312,6 +1399,25 @@ int abg_mixer_device_buffers(abg_engine* e, float** dev_sums, int32_t** dev_flag
     if (e->n_mixers <= 0) return fail(ABG_EINVAL, "abg_mixer_device_buffers: no mixers configured");
     if (dev_sums) *dev_sums = e->mix_sums.p;
     if (dev_flags) *dev_flags = e->mix_flags.p;
+    return ABG_OK;
+}
+
+// Host-only (no device needed): the tensor-core K1's plan and coefficient table for one device, exactly as abg_create
+// builds them.  plan[12] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo}.  tab may be null to
+// query the plan; otherwise tab_cap >= K*NC bytes and sq has C2p entries.
+int abg_debug_tc_table(int fft_size, int sfmt, int hop_bytes, float fullscale, int n_channels, const int32_t* bins, int digits, int32_t* plan,
+                       signed char* tab, size_t tab_cap, long long* sq, double* cscale) {
+    K1TcPlan p;
+    abg_k1tc_plan(fft_size, sfmt, hop_bytes, n_channels, digits, &p);
+    const int32_t v[12] = {p.eligible, p.K, p.HC, p.S, p.NC, p.ND, p.C2p, p.KBS, p.NSTB, p.tmem_cols, p.smem_bytes, p.halo};
+    if (plan) memcpy(plan, v, sizeof(v));
+    if (!p.eligible) return fail(ABG_EINVAL, "abg_debug_tc_table: configuration not eligible for the tensor-core K1");
+    if (!tab) return ABG_OK;
+    if (tab_cap < p.table_bytes || !sq || !cscale || !bins) return fail(ABG_EINVAL, "abg_debug_tc_table: buffers too small");
+    std::vector<float> wsc = make_window(fft_size);
+    const float scale = sample_scale(sfmt, fullscale);
+    for (auto& w : wsc) w = w * scale;
+    abg_k1tc_build_table(p, fft_size, sfmt, wsc.data(), bins, n_channels, tab, sq, cscale);
     return ABG_OK;
 }
 

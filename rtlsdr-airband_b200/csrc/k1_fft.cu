@@ -311,12 +311,15 @@ cudaError_t launch_one(const K1Launch& L, const K1Args& args, cudaStream_t s) {
     using P = Plan<LOGN>;
     const size_t smem = k1_fixed_smem<LOGN>() + (size_t)L.tile_bytes_cap;
     auto kern = k1_fft_kernel<LOGN, SFMT>;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static AbgPerDeviceSize configured;  // per instantiation, per CUDA device
+    {
+        cudaError_t e = configured.ensure(smem, [&]() {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return cudaSuccess;
+        });
         if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = smem;
     }
     const int tiles = (L.max_frames + L.frames_per_tile - 1) / L.frames_per_tile;
     dim3 grid(tiles, L.n_devices, 1), block(P::BLOCK, 1, 1);

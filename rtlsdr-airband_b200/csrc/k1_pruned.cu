@@ -320,12 +320,15 @@ cudaError_t pr_launch_one2(const K1Launch& L, const PrArgs& args, cudaStream_t s
     }
     if (max_ctas > 0) smem = std::max(smem, (size_t)(228 * 1024 / (max_ctas + 1) + 1024));
     auto kern = k1_pruned_kernel<LOGN, SFMT, R1, GE>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static AbgPerDeviceSize configured;  // per instantiation, per CUDA device
+    {
+        cudaError_t e = configured.ensure(smem, [&]() {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return cudaSuccess;
+        });
         if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = smem;
     }
     const int tiles = (L.max_frames + L.frames_per_tile - 1) / L.frames_per_tile;
     dim3 grid(tiles, L.n_devices, 1), block(PR_WARPS * 32, 1, 1);

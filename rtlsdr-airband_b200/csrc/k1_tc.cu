@@ -1,0 +1,419 @@
+// K1 (tensor-core) — sample conversion + window + DFT of the configured bins as ONE integer GEMM on the 5th-generation
+// tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), sm_100a.  Same inputs, same outputs as k1_pruned.cu /
+// k1_fft.cu; replaces the same reference code (reference src/rtl_airband.cpp:402-455 convert+window, :460
+// fftwf_execute, :483-489 bin extraction) for 8-bit sample formats (U8 / S8: RTL-SDR, file input).
+//
+// The reference transforms N points per frame and reads C bins.  Written out for one bin b of frame f,
+//     X[f,b] = sum_n  level(raw[f*hop + n]) * window[n] * W_N^(n*b)            (level(u) = (u - 127.5)/127.5 for U8)
+// is a dense contraction  [frames x 2N raw BYTES] x [2N x 2C coefficients]: the A operand is the device's raw byte
+// stream itself (8-bit integers are exact tensor-core operands: no conversion instruction is ever executed), the B operand
+// is window*twiddle quantised to ND signed 8-bit digits (ND = 4: 30-bit fixed point, |error| <= 2^-31 of the largest
+// coefficient, below the FP32 FFT's own rounding), accumulated EXACTLY in S32 and recombined in the epilogue:
+//     X = (Gmax / 2Q) * (2 * sum_d 256^(ND-1-d) * acc_d  -  255 * sum_k q_k)        (the -127.5 offset, folded out)
+//
+// Sliding windows without data movement: consecutive frames start hop_bytes apart (84 % overlap at N = 2048, hop 320).
+// The raw tile is stored in shared memory "transposed by 16-byte chunk": column j (of hop_bytes/16) holds bytes
+// [16j, 16j+16) of every hop-row r at AT[j][r], rows 16 bytes apart.  That IS the canonical K-major no-swizzle operand
+// layout (core matrix = 8 rows x 16 bytes), and the rows of frame f+q are the rows of frame f shifted by q*16 bytes, so
+// the MMA for K bytes [q*hop_bytes + 16j, +32) simply takes descriptor start address AT + j*S + q*16: every raw byte is
+// fetched from HBM once and written to shared memory once, and the tensor core reads it for each of the ~N/hop frames
+// containing it.
+//
+// One CTA per SM, persistent, dynamic tile queue (tile = 128 consecutive frames of one device), warp-specialised:
+//   warps 0-3  A producers: cp.async (LDGSTS) 16-byte chunks global -> transposed tile, double-buffered
+//   warps 4-7  epilogue: tcgen05.ld the S32 accumulators (double-buffered in TMEM), recombine digits in int64,
+//              one double multiply, |X| with the reference's rounding (rtl_airband.cpp:484), coalesced stores
+//   warp 8     tile scheduler (atomic counter) + B loader: the device's coefficient table streams through a ring of
+//              bulk-copy (TMA) stages, one pass per tile, out of L2
+//   warp 9     TMEM allocation + the single MMA-issuing thread
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "../../include/airband_b200.h"
+#include "abg_internal.h"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int TC_THREADS = 320;
+constexpr int TC_CTRL_BYTES = 1024;
+constexpr int TC_MAX_BSTAGES = 8;
+constexpr int TC_INFO_SLOTS = 4;
+
+struct TileInfo {
+    const unsigned char* src;  // first byte of the tile's first frame
+    int nf;                    // valid frames (1..128); <= 0: end of work
+    int pos;                   // row of win/iqin of the first frame
+    int gbase;                 // first channel index
+    int nch;                   // channels
+    int tab;                   // coefficient table
+    int pad;
+};
+
+struct TcArgs {
+    const K1Dev* devs;
+    const int32_t* tab_of_dev;
+    const signed char* btab;
+    const long long* sq;
+    float* win;
+    float2* iqin;
+    int* counter;
+    int32_t* status;
+    double cscale;
+    int Gp, n_devices, tiles_per_dev, total_tiles;
+    int K, hop_bytes, HC, S, NC, ND, C2p, KBS, NSTB, a_signed;
+    int mul, off;
+};
+
+struct Ctrl {
+    unsigned long long full_a[2], empty_a[2], tmem_full[2], tmem_empty[2];
+    unsigned long long full_b[TC_MAX_BSTAGES], empty_b[TC_MAX_BSTAGES];
+    unsigned long long info_full[TC_INFO_SLOTS], info_empty[TC_INFO_SLOTS];
+    TileInfo info[TC_INFO_SLOTS];
+    uint32_t tmem_base;
+    volatile int abort_flag;
+};
+static_assert(sizeof(Ctrl) <= TC_CTRL_BYTES, "control block too large");
+
+// bounded wait that also gives up when another role has flagged a protocol failure
+__device__ __forceinline__ bool tc_wait(Ctrl* c, uint32_t bar, uint32_t parity, int32_t* status, int code) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255) == 0) {
+            if (c->abort_flag) return false;
+            if (clock64() - t0 > (1ll << 30)) {
+                c->abort_flag = 1;
+                atomicExch(status, code);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Ctrl* c = reinterpret_cast<Ctrl*>(smem);
+    unsigned char* abuf = smem + TC_CTRL_BYTES;
+    const int abuf_bytes = a.HC * a.S;
+    unsigned char* bring = smem + TC_CTRL_BYTES + ((2 * abuf_bytes + 127) & ~127);
+    const int stage_bytes = a.KBS * a.NC * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int ACC_STRIDE = TMEM_COLS / 2;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(smem_u32(&c->full_a[i]), 128);
+            mbar_init(smem_u32(&c->empty_a[i]), 1);
+            mbar_init(smem_u32(&c->tmem_full[i]), 1);
+            mbar_init(smem_u32(&c->tmem_empty[i]), 128);
+        }
+        for (int i = 0; i < TC_MAX_BSTAGES; i++) {
+            mbar_init(smem_u32(&c->full_b[i]), 1);
+            mbar_init(smem_u32(&c->empty_b[i]), 1);
+        }
+        for (int i = 0; i < TC_INFO_SLOTS; i++) {
+            mbar_init(smem_u32(&c->info_full[i]), 1);
+            mbar_init(smem_u32(&c->info_empty[i]), 128);
+        }
+        c->abort_flag = 0;
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32(&c->tmem_base));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = c->tmem_base;
+    const int NKB = (a.K / 32) / a.KBS;  // B stages per tile
+
+    if (warp < 4) {
+        // ================= A producers =================
+        for (int it = 0;; ++it) {
+            const int slot = it & (TC_INFO_SLOTS - 1);
+            if (!tc_wait(c, smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1, a.status, 1)) break;
+            const TileInfo ti = c->info[slot];
+            if (ti.nf <= 0) break;
+            const int buf = it & 1;
+            if (!tc_wait(c, smem_u32(&c->empty_a[buf]), ((it >> 1) & 1) ^ 1, a.status, 2)) break;
+            const uint32_t dst0 = smem_u32(abuf + buf * abuf_bytes);
+            const int total_chunks = ((ti.nf - 1) * a.hop_bytes + a.K) >> 4;
+            int r = tid / a.HC, j = tid - r * a.HC;
+            const int dr = 128 / a.HC, dj = 128 - dr * a.HC;
+            for (int i = tid; i < total_chunks; i += 128) {
+                cp_async16(dst0 + j * a.S + r * 16, ti.src + (size_t)i * 16);
+                r += dr;
+                j += dj;
+                if (j >= a.HC) {
+                    j -= a.HC;
+                    r++;
+                }
+            }
+            cp_async_wait_all();
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&c->full_a[buf]));
+        }
+    } else if (warp < 8) {
+        // ================= epilogue =================
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        for (int it = 0;; ++it) {
+            const int slot = it & (TC_INFO_SLOTS - 1);
+            if (!tc_wait(c, smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1, a.status, 3)) break;
+            const TileInfo ti = c->info[slot];
+            if (ti.nf <= 0) break;
+            const int acc = it & 1;
+            if (!tc_wait(c, smem_u32(&c->tmem_full[acc]), (it >> 1) & 1, a.status, 4)) break;
+            tc_fence_after();
+            const uint32_t t0 = tmem + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)lane_base << 16);
+            const long long* sq = a.sq + (size_t)ti.tab * a.C2p;
+            const size_t orow = (size_t)(ti.pos + row) * a.Gp + ti.gbase;
+            const bool valid = row < ti.nf;
+            const bool vec = ((ti.gbase & 3) == 0) && ((a.Gp & 3) == 0);
+            for (int og = 0; og < a.C2p; og += 8) {
+                long long v[8];
+                for (int d = 0; d < a.ND; d++) {
+                    uint32_t rr[8];
+                    tmem_ld8(t0 + (uint32_t)(d * a.C2p + og), rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = (d == 0) ? (long long)(int32_t)rr[k] : (v[k] << 8) + (long long)(int32_t)rr[k];
+                }
+                float x[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = (float)((double)(a.mul * v[k] - a.off * __ldg(sq + og + k)) * a.cscale);
+                if (valid) {
+                    const int c0 = og >> 1;  // first channel of this group of four
+                    float m[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        m[k] = sqrtf(__fadd_rn(__fmul_rn(x[2 * k], x[2 * k]), __fmul_rn(x[2 * k + 1], x[2 * k + 1])));  // rtl_airband.cpp:484
+                    if (vec && c0 + 4 <= ti.nch) {
+                        *reinterpret_cast<float4*>(a.win + orow + c0) = make_float4(m[0], m[1], m[2], m[3]);
+                        float4* q = reinterpret_cast<float4*>(a.iqin + orow + c0);
+                        q[0] = make_float4(x[0], x[1], x[2], x[3]);
+                        q[1] = make_float4(x[4], x[5], x[6], x[7]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (c0 + k < ti.nch) {
+                                a.win[orow + c0 + k] = m[k];
+                                a.iqin[orow + c0 + k] = make_float2(x[2 * k], x[2 * k + 1]);
+                            }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&c->tmem_empty[acc]));
+            mbar_arrive(smem_u32(&c->info_empty[slot]));
+        }
+    } else if (warp == 8) {
+        // ================= tile scheduler + B loader =================
+        if (lane == 0) {
+            const size_t tab_bytes = (size_t)a.K * a.NC;
+            auto publish = [&](int it) -> int {  // claim the next tile and publish it in slot it % 4; returns its table or -1
+                const int slot = it & (TC_INFO_SLOTS - 1);
+                if (!tc_wait(c, smem_u32(&c->info_empty[slot]), ((it / TC_INFO_SLOTS) & 1) ^ 1, a.status, 5)) return -2;
+                TileInfo ti{};
+                ti.nf = 0;
+                ti.tab = -1;
+                for (;;) {
+                    const int t = atomicAdd(a.counter, 1);
+                    if (t >= a.total_tiles) break;
+                    const int dev = t / a.tiles_per_dev, st = t - dev * a.tiles_per_dev;
+                    const K1Dev dv = a.devs[dev];
+                    const int f0 = st * 128;
+                    if (f0 >= dv.n_frames || dv.n_channels <= 0) continue;
+                    ti.src = dv.raw + dv.start_byte + (unsigned long long)f0 * dv.hop_bytes;
+                    ti.nf = min(128, dv.n_frames - f0);
+                    ti.pos = dv.pos0 + f0;
+                    ti.gbase = dv.g0;
+                    ti.nch = dv.n_channels;
+                    ti.tab = a.tab_of_dev[dev];
+                    break;
+                }
+                c->info[slot] = ti;
+                mbar_arrive(smem_u32(&c->info_full[slot]));
+                return ti.tab;
+            };
+            int bcount = 0;
+            int tab = publish(0);
+            for (int it = 0; tab >= 0; ++it) {
+                const int next_tab = publish(it + 1);  // the A producers start on tile it+1 while tile it's coefficients stream
+                const signed char* src = a.btab + (size_t)tab * tab_bytes;
+                bool ok = true;
+                for (int kb = 0; kb < NKB && ok; kb++, bcount++) {
+                    const int stg = bcount % a.NSTB;
+                    ok = tc_wait(c, smem_u32(&c->empty_b[stg]), ((bcount / a.NSTB) & 1) ^ 1, a.status, 6);
+                    if (!ok) break;
+                    mbar_arrive_expect_tx(smem_u32(&c->full_b[stg]), (uint32_t)stage_bytes);
+                    bulk_g2s(smem_u32(bring + (size_t)stg * stage_bytes), src + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, smem_u32(&c->full_b[stg]));
+                }
+                if (!ok || next_tab == -2) break;
+                tab = next_tab;
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_i8(128, a.NC, a.a_signed, 1);
+            int bcount = 0;
+            for (int it = 0;; ++it) {
+                const int slot = it & (TC_INFO_SLOTS - 1);
+                if (!tc_wait(c, smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1, a.status, 7)) break;
+                if (c->info[slot].nf <= 0) break;
+                const int buf = it & 1;
+                if (!tc_wait(c, smem_u32(&c->full_a[buf]), (it >> 1) & 1, a.status, 8)) break;
+                if (!tc_wait(c, smem_u32(&c->tmem_empty[buf]), ((it >> 1) & 1) ^ 1, a.status, 9)) break;
+                fence_proxy_async();
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * ACC_STRIDE);
+                const uint32_t a0 = smem_u32(abuf + buf * abuf_bytes);
+                int q = 0, j = 0;
+                uint32_t accumulate = 0;
+                bool ok = true;
+                for (int kb = 0; kb < NKB; kb++, bcount++) {
+                    const int stg = bcount % a.NSTB;
+                    ok = tc_wait(c, smem_u32(&c->full_b[stg]), (bcount / a.NSTB) & 1, a.status, 10);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t b0 = smem_u32(bring + (size_t)stg * stage_bytes);
+                    for (int ks = 0; ks < a.KBS; ks++) {
+                        const uint64_t adesc = smem_desc_noswizzle(a0 + (uint32_t)(j * a.S + q * 16), (uint32_t)a.S, 128u);
+                        const uint64_t bdesc = smem_desc_noswizzle(b0 + (uint32_t)(ks * a.NC * 32), (uint32_t)a.NC * 16u, 128u);
+                        mma_i8(d_tmem, adesc, bdesc, idesc, accumulate);
+                        accumulate = 1;
+                        j += 2;
+                        if (j >= a.HC) {
+                            j = 0;
+                            q++;
+                        }
+                    }
+                    mma_commit(smem_u32(&c->empty_b[stg]));
+                }
+                if (!ok) break;
+                mma_commit(smem_u32(&c->empty_a[buf]));
+                mma_commit(smem_u32(&c->tmem_full[buf]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+template <int TMEM_COLS>
+cudaError_t tc_launch_cols(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
+    auto kern = k1_tc_kernel<TMEM_COLS>;
+    static AbgPerDeviceSize configured;  // per instantiation, per CUDA device
+    cudaError_t e = configured.ensure(smem, [&]() {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e2 != cudaSuccess) return e2;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return cudaSuccess;
+    });
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TC_THREADS, smem, s>>>(args);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Geometry of the tensor-core K1 for one launch group, or eligible == 0 when the group has to use the CUDA-core kernels.
+int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int digits, K1TcPlan* p) {
+    *p = K1TcPlan{};
+    if (sfmt != ABG_SFMT_U8 && sfmt != ABG_SFMT_S8) return 0;  // 16/32-bit formats stay on the FP32 kernels
+    if (hop_bytes % 32 != 0 || hop_bytes < 32) return 0;        // both 16-byte chunks of an MMA's K slice must lie in one hop-row
+    if (digits != 3 && digits != 4) return 0;
+    const int K = fft_size * 2;
+    const int HC = hop_bytes / 16;
+    const int halo = (K - 32) / hop_bytes;                      // extra hop-rows the last frame of a tile reaches into
+    int rows = 128 + halo;
+    if ((rows & 1) == 0) rows++;                                // odd 16-byte pitch: conflict-free transposed writes
+    const int S = rows * 16;
+    const int C2p = (2 * max_channels + 7) & ~7;
+    const int NC = (digits * C2p + 15) & ~15;
+    if (NC > 256) return 0;
+    int KBS = std::max(1, 4096 / (NC * 32));
+    while ((K / 32) % KBS) KBS >>= 1;
+    const int stage = KBS * NC * 32;
+    const size_t base = TC_CTRL_BYTES + (((size_t)2 * HC * S + 127) & ~(size_t)127);
+    const size_t cap = 212 * 1024;                               // leaves room for K2's one-warp CTAs on the same SM
+    const size_t hard_cap = 227 * 1024;
+    int nstb = (int)std::min<size_t>(TC_MAX_BSTAGES, base < cap ? (cap - base) / stage : 0);
+    if (nstb < 2) nstb = (int)std::min<size_t>(TC_MAX_BSTAGES, base < hard_cap ? (hard_cap - base) / stage : 0);
+    if (nstb < 2) return 0;
+    int cols = 32;
+    while (cols < NC) cols <<= 1;
+    p->eligible = 1; p->K = K; p->HC = HC; p->S = S; p->NC = NC; p->ND = digits; p->C2p = C2p; p->KBS = KBS; p->NSTB = nstb;
+    p->tmem_cols = 2 * cols; p->smem_bytes = (int)(base + (size_t)nstb * stage); p->halo = halo;
+    p->table_bytes = (size_t)K * NC;
+    return 1;
+}
+
+// Coefficient table of one device for the plan: tab[K * NC] signed digits in the shared-memory image the MMA reads
+// ([k-step][16-byte chunk][column][16 bytes]), sq[C2p] = sum over K of the quantised coefficient per output, and the scale
+// that turns the recombined integer into the reference's float (returned through *cscale; identical for every table of
+// the group).  wsc[n] = window[n] * 1/full-scale (reference src/rtl_airband.cpp:319-324,335-351).
+void abg_k1tc_build_table(const K1TcPlan& p, int fft_size, int sfmt, const float* wsc, const int32_t* bins, int n_channels, signed char* tab,
+                          long long* sq, double* cscale) {
+    const int N = fft_size, K = p.K, NC = p.NC, ND = p.ND;
+    double gmax = 0.0;
+    for (int n = 0; n < N; n++) gmax = std::max(gmax, fabs((double)wsc[n]));
+    if (gmax <= 0.0) gmax = 1.0;
+    const double Q = ldexp(1.0, 8 * ND - 2);
+    std::fill(tab, tab + (size_t)K * NC, (signed char)0);
+    for (int o = 0; o < p.C2p; o++) sq[o] = 0;
+    for (int c = 0; c < n_channels; c++) {
+        const int b = bins[c] & (N - 1);
+        for (int n = 0; n < N; n++) {
+            const double th = 2.0 * M_PI * (double)(((long long)n * b) % N) / (double)N;
+            const double w = (double)wsc[n], cs = cos(th) * w, sn = sin(th) * w;
+            // (I + iQ) * w * (cos - i sin):  Re = I*cs + Q*sn,  Im = -I*sn + Q*cs
+            const double coef[2][2] = {{cs, sn}, {-sn, cs}};  // [re/im output][I/Q input]
+            for (int reim = 0; reim < 2; reim++)
+                for (int comp = 0; comp < 2; comp++) {
+                    const int o = 2 * c + reim;
+                    const int kk = 2 * n + comp;
+                    long long q = llround(coef[reim][comp] / gmax * Q);
+                    sq[o] += q;
+                    const int ks = kk >> 5, h = (kk >> 4) & 1, t = kk & 15;
+                    for (int d = ND - 1; d >= 0; d--) {  // balanced base-256 digits, least significant first
+                        long long dig = ((q + 128) & 255) - 128;
+                        q = (q - dig) >> 8;
+                        tab[((size_t)(ks * 2 + h) * NC + (size_t)(d * p.C2p + o)) * 16 + t] = (signed char)dig;
+                    }
+                }
+        }
+    }
+    // U8: X = (gmax / 2Q) * (2v - 255 * sq);  S8: X = (gmax / Q) * v
+    *cscale = (sfmt == ABG_SFMT_U8) ? gmax / (2.0 * Q) : gmax / Q;
+}
+
+cudaError_t abg_launch_k1_tc(const K1Launch& L, const K1TcPlan& p, const K1TcTables& T, int sm_count, cudaStream_t s) {
+    TcArgs a{};
+    a.devs = L.devs; a.tab_of_dev = T.tab_of_dev; a.btab = T.btab; a.sq = T.sq; a.win = L.win; a.iqin = L.iqin; a.counter = T.counter;
+    a.status = T.status; a.cscale = T.cscale; a.Gp = L.Gp; a.n_devices = L.n_devices;
+    a.tiles_per_dev = (L.max_frames + 127) / 128;
+    a.total_tiles = a.tiles_per_dev * L.n_devices;
+    a.K = p.K; a.hop_bytes = p.HC * 16; a.HC = p.HC; a.S = p.S; a.NC = p.NC; a.ND = p.ND; a.C2p = p.C2p; a.KBS = p.KBS; a.NSTB = p.NSTB;
+    a.a_signed = (L.sfmt == ABG_SFMT_S8) ? 1 : 0;
+    a.mul = a.a_signed ? 1 : 2;
+    a.off = a.a_signed ? 0 : 255;
+    if (a.total_tiles <= 0) return cudaSuccess;
+    const int grid = std::min(a.total_tiles, std::max(sm_count, 1));
+    switch (p.tmem_cols) {
+        case 64: return tc_launch_cols<64>(a, grid, (size_t)p.smem_bytes, s);
+        case 128: return tc_launch_cols<128>(a, grid, (size_t)p.smem_bytes, s);
+        case 256: return tc_launch_cols<256>(a, grid, (size_t)p.smem_bytes, s);
+        case 512: return tc_launch_cols<512>(a, grid, (size_t)p.smem_bytes, s);
+    }
+    return cudaErrorInvalidValue;
+}

@@ -22,7 +22,7 @@ SYMBOLS = [
     "abg_last_error", "abg_version", "abg_create", "abg_destroy", "abg_wave_batch", "abg_hop", "abg_push",
     "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_fetch_batches", "abg_get_stats", "abg_set_bin",
     "abg_resident_load", "abg_run_resident", "abg_set_stream", "abg_launch_count", "abg_mixers_configure",
-    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline", "abg_scan_configure", "abg_scan_select", "abg_host_register", "abg_host_unregister", "abg_ingest_sync",
+    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline", "abg_scan_configure", "abg_scan_select", "abg_host_register", "abg_host_unregister", "abg_ingest_sync", "abg_fft_path", "abg_debug_tc_table",
 ]
 
 
@@ -90,6 +90,9 @@ def load():
     L.abg_scan_configure.restype, L.abg_scan_configure.argtypes = i, [vp, i, i, i, vp]
     L.abg_scan_select.restype, L.abg_scan_select.argtypes = i, [vp, i, i, i]
     L.abg_debug_timeline.restype, L.abg_debug_timeline.argtypes = i, [vp, i, C.POINTER(C.c_float)]
+    L.abg_fft_path.restype, L.abg_fft_path.argtypes = i, [vp, i]
+    L.abg_debug_tc_table.restype = i
+    L.abg_debug_tc_table.argtypes = [i, i, i, f, i, vp, i, vp, vp, C.c_size_t, vp, C.POINTER(C.c_double)]
     _LIB = L
     return L
 
@@ -186,6 +189,10 @@ class Engine:
         self._chk(self.L.abg_get_stats(self.h, dev, chan, C.byref(s)))
         return s
 
+    def fft_path(self, dev: int) -> int:
+        """1 full-spectrum FFT, 2 output-pruned FFT, 3 tensor-core DFT (which K1 the device's frames go through)."""
+        return self._chk(self.L.abg_fft_path(self.h, dev))
+
     def set_bin(self, dev: int, chan: int, bin_: int) -> None:
         self._chk(self.L.abg_set_bin(self.h, dev, chan, bin_))
 
@@ -262,6 +269,28 @@ class Engine:
         raw_frame = np.ascontiguousarray(raw_frame)
         self._chk(self.L.abg_debug_frame(self.h, dev, _ptr(raw_frame), _ptr(out)))
         return out.view(np.complex64)
+
+
+TC_PLAN_FIELDS = ("eligible", "K", "HC", "S", "NC", "ND", "C2p", "KBS", "NSTB", "tmem_cols", "smem_bytes", "halo")
+
+
+def tc_table(fft_size: int, sfmt: int, hop_bytes: int, bins: Sequence[int], digits: int = 4, fullscale: float = 1.0):
+    """Host-only view of the tensor-core K1's plan and coefficient table (abg_debug_tc_table).  Returns (plan dict,
+    tab int8[K/32, 2, NC, 16], sq int64[C2p], cscale) or (plan, None, None, None) when the shape is not eligible."""
+    L = load()
+    plan = np.zeros(12, np.int32)
+    b = np.asarray(bins, np.int32)
+    L.abg_debug_tc_table(fft_size, sfmt, hop_bytes, fullscale, len(b), _ptr(b), digits, _ptr(plan), None, 0, None, None)
+    pd = dict(zip(TC_PLAN_FIELDS, (int(x) for x in plan)))
+    if not pd["eligible"]:
+        return pd, None, None, None
+    tab = np.zeros(pd["K"] * pd["NC"], np.int8)
+    sq = np.zeros(pd["C2p"], np.int64)
+    cs = C.c_double(0.0)
+    rc = L.abg_debug_tc_table(fft_size, sfmt, hop_bytes, fullscale, len(b), _ptr(b), digits, _ptr(plan), _ptr(tab), tab.nbytes, _ptr(sq), C.byref(cs))
+    if rc < 0:
+        raise AbgError(rc, (L.abg_last_error() or b"").decode())
+    return pd, tab.reshape(pd["K"] // 32, 2, pd["NC"], 16), sq, cs.value
 
 
 def demodulate_all(cfg: Config, raws: List[np.ndarray], *, max_batches_per_run: int = 4, chunk_batches: int = 0, **kw):
