@@ -278,7 +278,7 @@ struct Slot {
 struct abg_engine {
     int N = 0, W = 0, B = 0, fm_demod = 0, nbmax = 4, P = 0, G = 0, Gp = 0, fft_mode = 0;
     int cuda_dev = 0, sm_count = 148, tc_digits = 4;
-    bool tc_auto = false;              // fft_mode 0 picks the tensor-core K1 for eligible groups
+    bool tc_auto = true;               // fft_mode 0 picks the tensor-core K1 for eligible groups (ABG_K1_TC_AUTO=0: FP32 kernels only)
     int32_t* tc_status = nullptr;      // pinned + mapped: the tensor-core K1 reports a stalled pipeline here (never hangs)
     int32_t* tc_status_dev = nullptr;
     bool any_iq_out = false;

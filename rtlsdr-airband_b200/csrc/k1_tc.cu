@@ -42,7 +42,7 @@ using namespace tc;
 
 constexpr int TC_THREADS = 320;
 constexpr int TC_CTRL_BYTES = 1024;
-constexpr int TC_MAX_BSTAGES = 8;
+constexpr int TC_MAX_BSTAGES = 16;
 constexpr int TC_INFO_SLOTS = 4;
 
 struct TileInfo {
@@ -68,6 +68,9 @@ struct TcArgs {
     int Gp, n_devices, tiles_per_dev, total_tiles;
     int K, hop_bytes, HC, S, NC, ND, C2p, KBS, NSTB, a_signed;
     int mul, off;
+    uint16_t aoff[512];        // per k-step start-address offset of the A operand, 16-byte units (K <= 16384)
+    int stage_in_row;          // every B stage's k-steps lie inside one hop-row (HC/2 is a multiple of KBS)
+    int rotate;                // start every CTA's K loop at a different coefficient block (exact integer sums commute)
 };
 
 struct Ctrl {
@@ -76,36 +79,18 @@ struct Ctrl {
     unsigned long long info_full[TC_INFO_SLOTS], info_empty[TC_INFO_SLOTS];
     TileInfo info[TC_INFO_SLOTS];
     uint32_t tmem_base;
-    volatile int abort_flag;
 };
 static_assert(sizeof(Ctrl) <= TC_CTRL_BYTES, "control block too large");
 
-// bounded wait that also gives up when another role has flagged a protocol failure
-__device__ __forceinline__ bool tc_wait(Ctrl* c, uint32_t bar, uint32_t parity, int32_t* status, int code) {
-    if (mbar_try_wait(bar, parity)) return true;
-    const long long t0 = clock64();
-    int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255) == 0) {
-            if (c->abort_flag) return false;
-            if (clock64() - t0 > (1ll << 30)) {
-                c->abort_flag = 1;
-                atomicExch(status, code);
-                return false;
-            }
-        }
-    }
-    return true;
-}
-
-template <int TMEM_COLS>
+// Every wait below is mbar_wait_spin: bounded inside one asm statement, traps instead of hanging (tc_ptx.cuh).
+template <int TMEM_COLS, int KBS>
 __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Ctrl* c = reinterpret_cast<Ctrl*>(smem);
     unsigned char* abuf = smem + TC_CTRL_BYTES;
     const int abuf_bytes = a.HC * a.S;
     unsigned char* bring = smem + TC_CTRL_BYTES + ((2 * abuf_bytes + 127) & ~127);
-    const int stage_bytes = a.KBS * a.NC * 32;
+    const int stage_bytes = KBS * a.NC * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int ACC_STRIDE = TMEM_COLS / 2;
 
@@ -124,7 +109,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             mbar_init(smem_u32(&c->info_full[i]), 1);
             mbar_init(smem_u32(&c->info_empty[i]), 128);
         }
-        c->abort_flag = 0;
         fence_mbar_init();
     }
     if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32(&c->tmem_base));
@@ -132,17 +116,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = c->tmem_base;
-    const int NKB = (a.K / 32) / a.KBS;  // B stages per tile
+    const int NKB = (a.K / 32) / KBS;  // B stages per tile
+    // All CTAs stream the same (or a few) coefficient tables out of L2 at the same pace: starting each CTA at a different
+    // block spreads the requests over the L2 slices (exact integer sums commute, so the K order is free).
+    const int kb_rot = a.rotate ? (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)NKB) : 0;
 
     if (warp < 4) {
         // ================= A producers =================
         for (int it = 0;; ++it) {
             const int slot = it & (TC_INFO_SLOTS - 1);
-            if (!tc_wait(c, smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1, a.status, 1)) break;
+            mbar_wait_spin(smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1);
             const TileInfo ti = c->info[slot];
             if (ti.nf <= 0) break;
             const int buf = it & 1;
-            if (!tc_wait(c, smem_u32(&c->empty_a[buf]), ((it >> 1) & 1) ^ 1, a.status, 2)) break;
+            mbar_wait_spin(smem_u32(&c->empty_a[buf]), ((it >> 1) & 1) ^ 1);
             const uint32_t dst0 = smem_u32(abuf + buf * abuf_bytes);
             const int total_chunks = ((ti.nf - 1) * a.hop_bytes + a.K) >> 4;
             int r = tid / a.HC, j = tid - r * a.HC;
@@ -166,11 +153,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
         const int row = lane_base + lane;
         for (int it = 0;; ++it) {
             const int slot = it & (TC_INFO_SLOTS - 1);
-            if (!tc_wait(c, smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1, a.status, 3)) break;
+            mbar_wait_spin(smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1);
             const TileInfo ti = c->info[slot];
             if (ti.nf <= 0) break;
             const int acc = it & 1;
-            if (!tc_wait(c, smem_u32(&c->tmem_full[acc]), (it >> 1) & 1, a.status, 4)) break;
+            mbar_wait_spin(smem_u32(&c->tmem_full[acc]), (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t0 = tmem + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)lane_base << 16);
             const long long* sq = a.sq + (size_t)ti.tab * a.C2p;
@@ -215,93 +202,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             mbar_arrive(smem_u32(&c->info_empty[slot]));
         }
     } else if (warp == 8) {
-        // ================= tile scheduler + B loader =================
-        if (lane == 0) {
-            const size_t tab_bytes = (size_t)a.K * a.NC;
-            auto publish = [&](int it) -> int {  // claim the next tile and publish it in slot it % 4; returns its table or -1
-                const int slot = it & (TC_INFO_SLOTS - 1);
-                if (!tc_wait(c, smem_u32(&c->info_empty[slot]), ((it / TC_INFO_SLOTS) & 1) ^ 1, a.status, 5)) return -2;
-                TileInfo ti{};
-                ti.nf = 0;
-                ti.tab = -1;
-                for (;;) {
-                    const int t = atomicAdd(a.counter, 1);
-                    if (t >= a.total_tiles) break;
-                    const int dev = t / a.tiles_per_dev, st = t - dev * a.tiles_per_dev;
-                    const K1Dev dv = a.devs[dev];
-                    const int f0 = st * 128;
-                    if (f0 >= dv.n_frames || dv.n_channels <= 0) continue;
-                    ti.src = dv.raw + dv.start_byte + (unsigned long long)f0 * dv.hop_bytes;
-                    ti.nf = min(128, dv.n_frames - f0);
-                    ti.pos = dv.pos0 + f0;
-                    ti.gbase = dv.g0;
-                    ti.nch = dv.n_channels;
-                    ti.tab = a.tab_of_dev[dev];
-                    break;
-                }
-                c->info[slot] = ti;
-                mbar_arrive(smem_u32(&c->info_full[slot]));
-                return ti.tab;
-            };
-            int bcount = 0;
-            int tab = publish(0);
-            for (int it = 0; tab >= 0; ++it) {
-                const int next_tab = publish(it + 1);  // the A producers start on tile it+1 while tile it's coefficients stream
-                const signed char* src = a.btab + (size_t)tab * tab_bytes;
-                bool ok = true;
-                for (int kb = 0; kb < NKB && ok; kb++, bcount++) {
-                    const int stg = bcount % a.NSTB;
-                    ok = tc_wait(c, smem_u32(&c->empty_b[stg]), ((bcount / a.NSTB) & 1) ^ 1, a.status, 6);
-                    if (!ok) break;
-                    mbar_arrive_expect_tx(smem_u32(&c->full_b[stg]), (uint32_t)stage_bytes);
-                    bulk_g2s(smem_u32(bring + (size_t)stg * stage_bytes), src + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, smem_u32(&c->full_b[stg]));
-                }
-                if (!ok || next_tab == -2) break;
-                tab = next_tab;
+        // ================= tile scheduler + B loader (whole warp in lock-step, one elected lane issues the copies) =================
+        const uint32_t leader = elect_one();
+        const size_t tab_bytes = (size_t)a.K * a.NC;
+        auto publish = [&](int it) -> int {  // lane 0: claim the next tile and publish it in slot it % 4; returns its table, -1 = no more
+            const int slot = it & (TC_INFO_SLOTS - 1);
+            mbar_wait_spin(smem_u32(&c->info_empty[slot]), ((it / TC_INFO_SLOTS) & 1) ^ 1);
+            TileInfo ti{};
+            ti.nf = 0;
+            ti.tab = -1;
+            for (;;) {
+                const int t = atomicAdd(a.counter, 1);
+                if (t >= a.total_tiles) break;
+                const int dev = t / a.tiles_per_dev, st = t - dev * a.tiles_per_dev;
+                const K1Dev dv = a.devs[dev];
+                const int f0 = st * 128;
+                if (f0 >= dv.n_frames || dv.n_channels <= 0) continue;
+                ti.src = dv.raw + dv.start_byte + (unsigned long long)f0 * dv.hop_bytes;
+                ti.nf = min(128, dv.n_frames - f0);
+                ti.pos = dv.pos0 + f0;
+                ti.gbase = dv.g0;
+                ti.nch = dv.n_channels;
+                ti.tab = a.tab_of_dev[dev];
+                break;
             }
+            c->info[slot] = ti;
+            mbar_arrive(smem_u32(&c->info_full[slot]));
+            return ti.tab;
+        };
+        uint32_t stg = 0, ph = 0;
+        const uint32_t fb_bar0 = smem_u32(&c->full_b[0]), eb_bar0 = smem_u32(&c->empty_b[0]);
+        uint32_t fb_bar = fb_bar0, eb_bar = eb_bar0, dst = smem_u32(bring);
+        int tab = lane == 0 ? publish(0) : 0;
+        tab = __shfl_sync(0xffffffffu, tab, 0);
+        for (int it = 0; tab >= 0; ++it) {
+            int next_tab = lane == 0 ? publish(it + 1) : 0;  // the A producers start on tile it+1 while tile it's coefficients stream
+            next_tab = __shfl_sync(0xffffffffu, next_tab, 0);
+            const signed char* src = a.btab + (size_t)tab * tab_bytes;
+            int kb = kb_rot;
+            for (int kbi = 0; kbi < NKB; kbi++) {
+                mbar_wait_spin(eb_bar, ph ^ 1);
+                if (leader) {
+                    mbar_arrive_expect_tx(fb_bar, (uint32_t)stage_bytes);
+                    bulk_g2s(dst, src + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, fb_bar);
+                }
+                if (++kb == NKB) kb = 0;
+                dst += (uint32_t)stage_bytes;
+                fb_bar += 8;
+                eb_bar += 8;
+                if (++stg == (uint32_t)a.NSTB) stg = 0, ph ^= 1, dst = smem_u32(bring), fb_bar = fb_bar0, eb_bar = eb_bar0;
+            }
+            tab = next_tab;
         }
     } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = idesc_i8(128, a.NC, a.a_signed, 1);
-            int bcount = 0;
-            for (int it = 0;; ++it) {
-                const int slot = it & (TC_INFO_SLOTS - 1);
-                if (!tc_wait(c, smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1, a.status, 7)) break;
-                if (c->info[slot].nf <= 0) break;
-                const int buf = it & 1;
-                if (!tc_wait(c, smem_u32(&c->full_a[buf]), (it >> 1) & 1, a.status, 8)) break;
-                if (!tc_wait(c, smem_u32(&c->tmem_empty[buf]), ((it >> 1) & 1) ^ 1, a.status, 9)) break;
-                fence_proxy_async();
+        // ================= MMA issuer (whole warp in lock-step, one elected lane issues) =================
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = idesc_i8(128, a.NC, a.a_signed, 1);
+        const int KSTEPS = a.K / 32;
+        uint32_t stg = 0, ph = 0;
+        // descriptor words that never change: LBO in bits [16,30) of the low word, SBO + version in the high word
+        const uint64_t adesc0 = smem_desc_noswizzle(0, (uint32_t)a.S, 128u), bdesc0 = smem_desc_noswizzle(0, (uint32_t)a.NC * 16u, 128u);
+        const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+        const uint32_t bstep16 = (uint32_t)(a.NC * 32) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+        const uint32_t b_lo_ring = (uint32_t)bdesc0 + (smem_u32(bring) >> 4);
+        uint32_t b_lo = b_lo_ring;
+        const uint32_t fb_bar0 = smem_u32(&c->full_b[0]), eb_bar0 = smem_u32(&c->empty_b[0]);
+        uint32_t fb_bar = fb_bar0, eb_bar = eb_bar0;
+        const uint32_t a_step = 2u * ((uint32_t)a.S >> 4);
+        for (int it = 0;; ++it) {
+            const int slot = it & (TC_INFO_SLOTS - 1);
+            mbar_wait_spin(smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1);
+            if (c->info[slot].nf <= 0) break;
+            const int buf = it & 1;
+            mbar_wait_spin(smem_u32(&c->full_a[buf]), (it >> 1) & 1);
+            mbar_wait_spin(smem_u32(&c->tmem_empty[buf]), ((it >> 1) & 1) ^ 1);
+            fence_proxy_async();
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + (uint32_t)(buf * ACC_STRIDE);
+            const uint32_t a_lo = (uint32_t)adesc0 + (smem_u32(abuf + buf * abuf_bytes) >> 4);
+            int ksg = kb_rot * KBS;  // k-step index inside the frame of the stage being consumed
+            for (int kbi = 0; kbi < NKB; kbi++) {
+                mbar_wait_spin(fb_bar, ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + (uint32_t)(buf * ACC_STRIDE);
-                const uint32_t a0 = smem_u32(abuf + buf * abuf_bytes);
-                int q = 0, j = 0;
-                uint32_t accumulate = 0;
-                bool ok = true;
-                for (int kb = 0; kb < NKB; kb++, bcount++) {
-                    const int stg = bcount % a.NSTB;
-                    ok = tc_wait(c, smem_u32(&c->full_b[stg]), (bcount / a.NSTB) & 1, a.status, 10);
-                    if (!ok) break;
-                    tc_fence_after();
-                    const uint32_t b0 = smem_u32(bring + (size_t)stg * stage_bytes);
-                    for (int ks = 0; ks < a.KBS; ks++) {
-                        const uint64_t adesc = smem_desc_noswizzle(a0 + (uint32_t)(j * a.S + q * 16), (uint32_t)a.S, 128u);
-                        const uint64_t bdesc = smem_desc_noswizzle(b0 + (uint32_t)(ks * a.NC * 32), (uint32_t)a.NC * 16u, 128u);
-                        mma_i8(d_tmem, adesc, bdesc, idesc, accumulate);
-                        accumulate = 1;
-                        j += 2;
-                        if (j >= a.HC) {
-                            j = 0;
-                            q++;
-                        }
+                if (a.stage_in_row) {
+                    // the stage's KBS k-steps lie in one hop-row: consecutive k-steps are two 16-byte columns apart
+                    const uint32_t base = a_lo + a.aoff[ksg];
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < KBS; ks++) mma_i8_split(d_tmem, base + ks * a_step, a_hi, b_lo + ks * bstep16, b_hi, idesc, (kbi | ks) ? 1u : 0u);
+                        mma_commit(eb_bar);
                     }
-                    mma_commit(smem_u32(&c->empty_b[stg]));
+                } else {
+                    uint32_t ao[KBS];
+#pragma unroll
+                    for (int ks = 0; ks < KBS; ks++) ao[ks] = a_lo + a.aoff[ksg + ks];
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < KBS; ks++) mma_i8_split(d_tmem, ao[ks], a_hi, b_lo + ks * bstep16, b_hi, idesc, (kbi | ks) ? 1u : 0u);
+                        mma_commit(eb_bar);
+                    }
                 }
-                if (!ok) break;
+                __syncwarp();
+                ksg += KBS;
+                if (ksg == KSTEPS) ksg = 0;  // wrapped around to the start of the frame
+                b_lo += stage16;
+                fb_bar += 8;
+                eb_bar += 8;
+                if (++stg == (uint32_t)a.NSTB) stg = 0, ph ^= 1, b_lo = b_lo_ring, fb_bar = fb_bar0, eb_bar = eb_bar0;
+            }
+            if (leader) {
                 mma_commit(smem_u32(&c->empty_a[buf]));
                 mma_commit(smem_u32(&c->tmem_full[buf]));
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -309,9 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
     if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-template <int TMEM_COLS>
-cudaError_t tc_launch_cols(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
-    auto kern = k1_tc_kernel<TMEM_COLS>;
+template <int TMEM_COLS, int KBS>
+cudaError_t tc_launch_one(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
+    auto kern = k1_tc_kernel<TMEM_COLS, KBS>;
     static AbgPerDeviceSize configured;  // per instantiation, per CUDA device
     cudaError_t e = configured.ensure(smem, [&]() {
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -322,6 +335,16 @@ cudaError_t tc_launch_cols(const TcArgs& args, int grid, size_t smem, cudaStream
     if (e != cudaSuccess) return e;
     kern<<<grid, TC_THREADS, smem, s>>>(args);
     return cudaGetLastError();
+}
+template <int TMEM_COLS>
+cudaError_t tc_launch_cols(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
+    switch (args.KBS) {
+        case 1: return tc_launch_one<TMEM_COLS, 1>(args, grid, smem, s);
+        case 2: return tc_launch_one<TMEM_COLS, 2>(args, grid, smem, s);
+        case 4: return tc_launch_one<TMEM_COLS, 4>(args, grid, smem, s);
+        case 8: return tc_launch_one<TMEM_COLS, 8>(args, grid, smem, s);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -341,14 +364,20 @@ int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int d
     const int C2p = (2 * max_channels + 7) & ~7;
     const int NC = (digits * C2p + 15) & ~15;
     if (NC > 256) return 0;
-    int KBS = std::max(1, 4096 / (NC * 32));
-    while ((K / 32) % KBS) KBS >>= 1;
+    int stage_target = 8192;
+    if (const char* ev = getenv("ABG_K1_TC_STAGE_BYTES")) stage_target = std::max(1024, atoi(ev));
+    if (K > 16384) return 0;
+    int KBS = 1;
+    while (KBS < 8 && KBS * 2 * NC * 32 <= stage_target) KBS <<= 1;  // power of two: divides K/32
     const int stage = KBS * NC * 32;
     const size_t base = TC_CTRL_BYTES + (((size_t)2 * HC * S + 127) & ~(size_t)127);
-    const size_t cap = 212 * 1024;                               // leaves room for K2's one-warp CTAs on the same SM
+    size_t cap = 200 * 1024;                                     // leaves room for K2's one-warp CTAs on the same SM (measured: best pipelined step)
+    if (const char* ev = getenv("ABG_K1_TC_CAP_KB")) cap = std::min<size_t>(227, std::max(64, atoi(ev))) * 1024;
+    int max_stages = TC_MAX_BSTAGES;
+    if (const char* ev = getenv("ABG_K1_TC_STAGES")) max_stages = std::min(TC_MAX_BSTAGES, std::max(2, atoi(ev)));
     const size_t hard_cap = 227 * 1024;
-    int nstb = (int)std::min<size_t>(TC_MAX_BSTAGES, base < cap ? (cap - base) / stage : 0);
-    if (nstb < 2) nstb = (int)std::min<size_t>(TC_MAX_BSTAGES, base < hard_cap ? (hard_cap - base) / stage : 0);
+    int nstb = (int)std::min<size_t>(max_stages, base < cap ? (cap - base) / stage : 0);
+    if (nstb < 2) nstb = (int)std::min<size_t>(max_stages, base < hard_cap ? (hard_cap - base) / stage : 0);
     if (nstb < 2) return 0;
     int cols = 32;
     while (cols < NC) cols <<= 1;
@@ -407,6 +436,14 @@ cudaError_t abg_launch_k1_tc(const K1Launch& L, const K1TcPlan& p, const K1TcTab
     a.a_signed = (L.sfmt == ABG_SFMT_S8) ? 1 : 0;
     a.mul = a.a_signed ? 1 : 2;
     a.off = a.a_signed ? 0 : 255;
+    a.rotate = 1;
+    a.stage_in_row = ((p.HC / 2) % p.KBS == 0) ? 1 : 0;
+    for (int ks = 0; ks < p.K / 32; ks++) {
+        // K bytes [32ks, 32ks+32) of a frame are the two 16-byte columns j, j+1 of hop-row q
+        const int k0 = ks * 32, q = k0 / a.hop_bytes, j = (k0 - q * a.hop_bytes) >> 4;
+        a.aoff[ks] = (uint16_t)(j * (p.S >> 4) + q);
+    }
+    if (const char* ev = getenv("ABG_K1_TC_ROTATE")) a.rotate = atoi(ev) != 0;
     if (a.total_tiles <= 0) return cudaSuccess;
     const int grid = std::min(a.total_tiles, std::max(sm_count, 1));
     switch (p.tmem_cols) {

@@ -17,6 +17,19 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a fully converged warp (the others get 0)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred)
+        :
+        : "memory");
+    return pred;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -47,6 +60,26 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, long lo
         if (clock64() - t0 > budget_cycles) return false;
     }
     return true;
+}
+
+// Spin inside ONE asm statement (so the compiler sees straight-line, warp-uniform code around it and keeps the role loops
+// on the uniform datapath), bounded: a barrier that never completes is a protocol bug and must not hang the GPU, so after
+// ~10^6 failed try_waits (each suspends up to the hardware's time limit) the kernel traps and the launch fails cleanly.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x100000;\n\t"
+        "@p bra WAIT_LOOP;\n\t"
+        "trap;\n"
+        "WAIT_DONE:\n\t}"
+        :
+        : "r"(bar), "r"(parity)
+        : "memory");
 }
 
 // ---- copies ---------------------------------------------------------------------------------------------------------
@@ -93,6 +126,20 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         :
         : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same, descriptors passed as 32-bit halves (the low word carries the start address and is the only part that changes
+// from one K step to the next: no 64-bit arithmetic in the issue loop)
+__device__ __forceinline__ void mma_i8_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies tcgen05.fence::before_thread_sync)
