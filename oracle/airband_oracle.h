@@ -79,6 +79,7 @@ int abo_push(void* h, int dev, const void* iq, size_t nbytes);
  * n_threads > 1 splits the device range across threads like multiple_demod_threads.  Returns batches produced. */
 long abo_run(void* h, int max_batches, int n_threads);
 void abo_set_discard(void* h, int discard); /* 1: do not queue outputs (timing runs) */
+void abo_set_pin(void* h, const int* cpus, int n); /* timing runs: worker thread t of abo_run is pinned to cpus[t % n] */
 int abo_batches_ready(void* h, int dev);
 /* pop the oldest finished batch of a device: waveout[C*B], iq_out[C*2*B] (may be NULL), axc[C]; 1 if popped */
 int abo_fetch_batch(void* h, int dev, float* waveout, float* iq_out, char* axc);

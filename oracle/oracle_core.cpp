@@ -32,6 +32,8 @@
 #include <cstdlib>
 #include <deque>
 #include <memory>
+#include <pthread.h>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
@@ -145,6 +147,7 @@ struct Device {
 struct Oracle {
     int fft_size, wave_rate, wave_batch, wave_len, fm_demod;
     bool discard = false;
+    std::vector<int> pin_cpus;  // worker thread t runs on pin_cpus[t % size] (timing runs; empty = scheduler's choice)
     std::vector<float> window;
     float levels_u8[256], levels_s8[256];
     std::vector<std::unique_ptr<Device>> devp;
@@ -494,6 +497,12 @@ long abo_run(void* h, int max_batches, int n_threads) {
     std::vector<std::thread> th;
     for (int t = 0; t < n_threads; t++) {
         th.emplace_back([&, t]() {
+            if (!o->pin_cpus.empty()) {
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                CPU_SET(o->pin_cpus[t % o->pin_cpus.size()], &set);
+                pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+            }
             Worker w(o->fft_size);
             // contiguous device ranges like init_demod(device_start, device_end), rtl_airband.cpp:1070-1086
             int lo = (int)((long)D * t / n_threads), hi = (int)((long)D * (t + 1) / n_threads);
@@ -507,6 +516,10 @@ long abo_run(void* h, int max_batches, int n_threads) {
 }
 
 void abo_set_discard(void* h, int discard) { ((Oracle*)h)->discard = discard != 0; }
+void abo_set_pin(void* h, const int* cpus, int n) {
+    Oracle* o = (Oracle*)h;
+    o->pin_cpus.assign(cpus, cpus + (n > 0 ? n : 0));
+}
 int abo_batches_ready(void* h, int dev) { return (int)((Oracle*)h)->D(dev).ready.size(); }
 
 int abo_fetch_batch(void* h, int dev, float* waveout, float* iq_out, char* axc) {

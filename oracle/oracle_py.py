@@ -61,6 +61,7 @@ def lib(variant: str = "restated"):
         "abo_push": (i, [vp, i, vp, C.c_size_t]),
         "abo_run": (C.c_long, [vp, i, i]),
         "abo_set_discard": (None, [vp, i]),
+        "abo_set_pin": (None, [vp, vp, i]),
         "abo_batches_ready": (i, [vp, i]),
         "abo_fetch_batch": (i, [vp, i, vp, vp, vp]),
         "abo_get_stats": (i, [vp, i, i, C.POINTER(CSquelchStats)]),
@@ -154,6 +155,11 @@ class Oracle:
 
     def run(self, max_batches: int = -1, n_threads: int = 1) -> int:
         return int(self.L.abo_run(self.h, max_batches, n_threads))
+
+    def set_pin(self, cpus) -> None:
+        """Pin abo_run's worker thread t to cpus[t % len(cpus)] (timing runs)."""
+        arr = np.ascontiguousarray(cpus, np.int32)
+        self.L.abo_set_pin(self.h, _ptr(arr), int(arr.size))
 
     def set_discard(self, flag: bool) -> None:
         self.L.abo_set_discard(self.h, 1 if flag else 0)
