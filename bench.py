@@ -101,6 +101,9 @@ def parse_cpulist(s: str):
     return out
 
 
+_ALL_CPUS = set(os.sched_getaffinity(0))  # what the process may use before any binding (restored for the CPU baseline leg)
+
+
 def bind_to_gpu_numa(gpu_index: int) -> dict:
     """Run this process (and place the pinned buffers it allocates from now on: first touch) on the CPUs of the NUMA node
     the GPU hangs off.  H2D copies from the far socket cross UPI and cap the 8-GPU end-to-end rate."""
@@ -116,7 +119,7 @@ def bind_to_gpu_numa(gpu_index: int) -> dict:
         allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
         if allowed:
             os.sched_setaffinity(0, allowed)
-            info = {"bound": True, "gpu_pci": bdf, "numa_node": node, "cpus": f"{allowed[0]}-{allowed[-1]} ({len(allowed)} cpus)"}
+            info = {"bound": True, "gpu_pci": bdf, "numa_node": node, "cpus": open(base + "/local_cpulist").read().strip(), "n_cpus": len(allowed)}
     except Exception as ex:  # no sysfs / no nvidia-smi: run unbound and say so
         info = {"bound": False, "why": str(ex)[:120]}
     return info
@@ -279,6 +282,10 @@ def cpu_run(cfg, desc, steps: int, warmup: int, budget_s: float = 20.0, extras: 
     import oracle_py as op
     variant = "ref_fast" if op.available("ref_fast") else "restated_fast"
     kind = "reference" if variant == "ref_fast" else "port"
+    try:
+        os.sched_setaffinity(0, _ALL_CPUS)  # the GPU arm binds itself to one NUMA node; the CPU arm gets every core of the box
+    except Exception:
+        pass
     cpu = cpu_description()
     cores = max(1, cpu["physical_cores"])
     D = min(len(cfg.devices), cores)
@@ -302,7 +309,7 @@ def cpu_run(cfg, desc, steps: int, warmup: int, budget_s: float = 20.0, extras: 
             info["extras_error"] = str(ex)[:200]
         finally:
             try:
-                os.sched_setaffinity(0, set(range(os.cpu_count() or 1)))
+                os.sched_setaffinity(0, _ALL_CPUS)
             except Exception:
                 pass
     return msps, info, dt / max(steps, 1) * 1e3

@@ -92,6 +92,9 @@ typedef struct abg_squelch_stats {
     uint32_t dm_phi;         /* channel_t.dm_phi */
     int32_t bin;             /* current dev->bins[i] */
     uint64_t active_counter; /* freq_t.active_counter, reference src/rtl_airband.cpp:645-647 */
+    /* the three levels as the stats file and the TUI print them: level_to_dBFS(), reference src/util.cpp:169-180
+     * (output.cpp:624-700 channel_dbfs_*_level gauges, rtl_airband.cpp:632-643) */
+    float noise_level_dbfs, signal_level_dbfs, squelch_level_dbfs;
 } abg_squelch_stats;
 
 /* Engine tuning (0 = default everywhere). */

@@ -68,6 +68,7 @@ typedef struct abo_squelch_stats {
     uint32_t dm_phi;  /* channel_t.dm_phi */
     int32_t bin;      /* current dev->bins[i] (AFC may have moved it) */
     uint64_t active_counter;
+    float noise_level_dbfs, signal_level_dbfs, squelch_level_dbfs; /* level_to_dBFS(), reference src/util.cpp:169-180 */
 } abo_squelch_stats;
 
 void* abo_create(const abo_config* cfg);

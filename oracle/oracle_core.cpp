@@ -552,6 +552,9 @@ int abo_get_stats(void* h, int dev, int chan, abo_squelch_stats* out) {
     out->dm_phi = c.dm_phi;
     out->bin = (int32_t)d.bins[chan];
     out->active_counter = f.active_counter;
+    out->noise_level_dbfs = abo_level_to_dbfs(out->noise_level, o->fft_size);
+    out->signal_level_dbfs = abo_level_to_dbfs(out->signal_level, o->fft_size);
+    out->squelch_level_dbfs = abo_level_to_dbfs(out->squelch_level, o->fft_size);
     return 0;
 }
 

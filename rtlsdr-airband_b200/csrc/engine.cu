@@ -1129,6 +1129,13 @@ int abg_get_stats(abg_engine* e, int dev, int chan, abg_squelch_stats* out) {
     out->dm_phi = s.dm_phi;
     out->bin = bin;
     out->active_counter = s.active_counter;
+    // level_to_dBFS(), util.cpp:169-180: min(0, 20*log10f(level / fft_size) + 7.54f + 10*log10f(fft_size / 2) - 2.38f)
+    const size_t fft_size = (size_t)e->N;
+    const float offset = 7.54f + 10.0f * log10f(fft_size / 2) - 2.38f;
+    auto to_dbfs = [&](float level) { return std::min(0.0f, 20.0f * log10f(level / fft_size) + offset); };
+    out->noise_level_dbfs = to_dbfs(out->noise_level);
+    out->signal_level_dbfs = to_dbfs(out->signal_level);
+    out->squelch_level_dbfs = to_dbfs(out->squelch_level);
     return ABG_OK;
 }
 

@@ -75,29 +75,58 @@ class Signal {  // rtl_airband.h:201-221
     pthread_mutex_t mutex_;
 };
 
+// What the WITH_B200 patch adds to the reference's freq_t (integration/reference_b200.patch): the values parse_channels()
+// hands to Squelch / NotchFilter / LowpassFilter (config.cpp:437-619; those objects have no getters), and the
+// Squelch read-outs the stats file / TUI use (squelch.h:89-96, output.cpp:598-869, rtl_airband.cpp:632-643), refreshed from
+// the engine by b200_refresh_stats().
+struct b200_freq_cfg {
+    float squelch_level, squelch_snr_db, notch_hz, notch_q, ctcss_hz, lowpass_hz;
+};
+struct b200_freq_stats {
+    float noise_level, signal_level, squelch_level;
+    float noise_level_dbfs, signal_level_dbfs, squelch_level_dbfs;  // level_to_dBFS(), util.cpp:178-180
+    size_t open_count, flappy_count, ctcss_count, no_ctcss_count;
+};
+
 struct freq_t {
     int frequency;
     float agcavgfast;  // mirrored back from the engine for the stats file
     float ampfactor;
     size_t active_counter;
     enum modulations modulation;
-    // what parse_channels() hands to Squelch / NotchFilter / LowpassFilter (config.cpp:437-619)
-    float squelch_level, squelch_snr_db, notch_hz, notch_q, ctcss_hz, lowpass_hz;
-    // Squelch getters the stats code reads (squelch.h:89-96)
-    float noise_level, signal_level, squelch_level_now;
-    size_t open_count, flappy_count, ctcss_count, no_ctcss_count;
+    b200_freq_cfg b200_cfg;
+    b200_freq_stats b200_stats;
+};
+
+enum ch_states { CH_DIRTY, CH_WORKING, CH_READY };  // rtl_airband.h:102
+enum mix_modes { MM_MONO, MM_STEREO };               // rtl_airband.h:103
+enum output_type { O_ICECAST, O_FILE, O_RAWFILE, O_MIXER, O_UDP_STREAM };  // rtl_airband.h:104-115
+struct output_t {  // rtl_airband.h:180-185
+    enum output_type type;
+    bool enabled;
+    bool active;
+    void* data;
+};
+struct mixer_data {  // rtl_airband.h:175-178
+    struct mixer_t* mixer;
+    int input;
 };
 
 struct channel_t {
-    float* waveout;  // [WAVE_LEN]; the consumer reads [0, WAVE_BATCH)
-    float* iq_out;   // [2 * WAVE_LEN]
+    float* waveout;    // [WAVE_LEN]; the consumer reads [0, WAVE_BATCH)
+    float* waveout_r;  // [WAVE_LEN] right channel of a stereo mixer (mixer channels only)
+    float* iq_out;     // [2 * WAVE_LEN]
     float alpha;
     uint32_t dm_dphi;
+    enum mix_modes mode;
     enum status axcindicate;
     unsigned char afc;
     freq_t* freqlist;
     int freq_count, freq_idx;
     int needs_raw_iq, has_iq_outputs;
+    enum ch_states state;  // mixer channel state flag (mixer.cpp:157-261 <-> output.cpp:888-896)
+    int output_count;
+    output_t* outputs;
 };
 
 struct device_t {
@@ -107,6 +136,21 @@ struct device_t {
     channel_t* channels;
     int waveavail;
     size_t output_overrun_count;
+};
+
+struct mixinput_t {  // rtl_airband.h:288-296 (the fields the hand-off reads)
+    float ampfactor;
+    float ampl, ampr;
+};
+struct mixer_t {  // rtl_airband.h:298-308
+    const char* name;
+    bool enabled;
+    int interval;
+    size_t output_overrun_count;
+    int input_count;
+    mixinput_t* inputs;
+    bool* input_mask;
+    channel_t channel;
 };
 
 struct demod_params_t {
@@ -119,6 +163,9 @@ struct demod_params_t {
 struct b200_globals {
     device_t* devices;
     int device_count;
+    mixer_t* mixers;          // rtl_airband.cpp:72
+    int mixer_count;
+    void (*on_device_failed)(device_t* dev);  // stands in for disable_device_outputs(dev), rtl_airband.cpp:386
     size_t fft_size;
     int wave_rate;            // WAVE_RATE as a run-time value
     int fm_demod;
@@ -134,5 +181,8 @@ extern b200_globals g_b200;
 // Drop-in for `void* demodulate(void* params)` (reference src/rtl_airband.cpp:286, started at :1111).
 extern "C" ABG_API void* demodulate_b200(void* params);
 
-// circbuffer_append (reference src/input-helpers.cpp:37-63), used by the test feeder
+// circbuffer_append (reference src/input-helpers.cpp:37-63): producer-side reference code, restated for the TEST feeders only
+// (host_harness.cpp); in the reference tree the real one is used and nothing here duplicates its symbol.
 void circbuffer_append(input_t* const input, unsigned char* buf, size_t len);
+
+// b200_refresh_stats / b200_deliver_mixers / b200_write_rawfile: see b200_adapter.h

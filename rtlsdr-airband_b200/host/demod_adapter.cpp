@@ -1,12 +1,19 @@
 // demodulate_b200(): the reference's demod thread function re-expressed over the C ABI of the B200 engine.
 // Same contract as demodulate() (reference src/rtl_airband.cpp:286-672): it owns devices[device_start..device_end),
 // consumes each input ring under the reference's locking discipline (:370-375, bufs advanced without the lock, :669),
-// follows the input state machine (:377-391), delivers finished batches into channel_t.waveout / iq_out /
-// axcindicate, bumps active_counter (:645-647), raises waveavail or counts an overrun (:649-654), and signals the
-// output thread (:662).  Fatal engine errors are reported like the VideoCore branch does (:296-310): message + exit.
-#include "airband_host.h"
+// follows the input state machine (:377-391, including disable_device_outputs() for a dead receiver), delivers finished
+// batches into channel_t.waveout / iq_out / axcindicate, bumps active_counter (:645-647), raises waveavail or counts an
+// overrun (:649-654), and signals the output thread (:662).  Mixers whose inputs all live on this thread's devices are
+// summed on the GPU and handed to the output thread through mixer_t.channel with the reference's CH_DIRTY -> CH_WORKING ->
+// CH_READY handshake (mixer.cpp:157-261 producer side, output.cpp:888-896 consumer side).  Fatal engine errors are
+// reported like the VideoCore branch does (:296-310): message + exit.
+//
+// One source, two bindings (b200_adapter.h): the reference's own structs (ABG_WITH_REFERENCE_HEADERS, inside the reference
+// tree) or the mirror of the same fields used by this repository's tests.
+#include "b200_adapter.h"
 
 #include <errno.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,10 +21,12 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <deque>
 #include <vector>
 
 b200_globals g_b200;
 
+#ifndef ABG_WITH_REFERENCE_HEADERS
 void Signal::wait_ms(int ms) {
     timespec ts;
     clock_gettime(CLOCK_REALTIME, &ts);
@@ -28,59 +37,131 @@ void Signal::wait_ms(int ms) {
     pthread_cond_timedwait(&cond_, &mutex_, &ts);
     pthread_mutex_unlock(&mutex_);
 }
-
-// reference src/input-helpers.cpp:37-63
-void circbuffer_append(input_t* const input, unsigned char* buf, size_t len) {
-    if (len == 0) return;
-    pthread_mutex_lock(&input->buffer_lock);
-    const size_t tail = 2 * input->bytes_per_sample * g_b200.fft_size;
-    size_t space_left = input->buf_size - input->bufe;
-    if (space_left >= len) {
-        memcpy(input->buffer + input->bufe, buf, len);
-        if (input->bufe == 0) memcpy(input->buffer + input->buf_size, input->buffer, std::min(len, tail));
-    } else {
-        memcpy(input->buffer + input->bufe, buf, space_left);
-        memcpy(input->buffer, buf + space_left, len - space_left);
-        memcpy(input->buffer + input->buf_size, input->buffer, std::min(len - space_left, tail));
-    }
-    size_t old_end = input->bufe;
-    input->bufe = (input->bufe + len) % input->buf_size;
-    if (old_end < input->bufs && input->bufe >= input->bufs) input->overflow_count++;
-    pthread_mutex_unlock(&input->buffer_lock);
-}
+#endif
 
 static void fatal(const char* what) {
     snprintf(g_b200.last_error, sizeof(g_b200.last_error), "%s: %s", what, abg_last_error());
-    fprintf(stderr, "%s\n", g_b200.last_error);  // log(LOG_CRIT, ...) in the reference tree
-    g_b200.do_exit = 1;                          // error() = _Exit(1) there; the test harness wants to survive
+#ifdef ABG_WITH_REFERENCE_HEADERS
+    log(LOG_CRIT, "%s\n", g_b200.last_error);
+    error();
+#else
+    fprintf(stderr, "%s\n", g_b200.last_error);
+    bd::exit_flag() = 1;  // error() = _Exit(1) in the reference tree; the test harness wants to survive
+#endif
 }
 
-// channel_t / freq_t -> abg_channel_cfg (what INTEGRATION.md calls b200_channel_cfg)
+// channel_t / freq_t -> abg_channel_cfg
 static void fill_channel_cfg(const device_t* dev, int c, const freq_t* f, abg_channel_cfg* out) {
     const channel_t* ch = dev->channels + c;
     abg_channel_cfg& o = *out;
     memset(&o, 0, sizeof(o));
     o.bin = (int32_t)dev->bins[c];
-    o.modulation = f->modulation == MOD_NFM ? ABG_MOD_NFM : ABG_MOD_AM;
+    o.modulation = bd::is_nfm(f) ? ABG_MOD_NFM : ABG_MOD_AM;
     o.needs_raw_iq = ch->needs_raw_iq;
     o.has_iq_outputs = ch->has_iq_outputs;
     o.dm_dphi = ch->dm_dphi;
-    o.alpha = ch->alpha;
+    o.alpha = bd::channel_alpha(ch);
     o.ampfactor = f->ampfactor;
-    o.squelch_level = f->squelch_level;
-    o.squelch_snr_db = f->squelch_snr_db;
-    o.lowpass_hz = f->lowpass_hz;
-    o.notch_hz = f->notch_hz;
-    o.notch_q = f->notch_q;
-    o.ctcss_hz = f->ctcss_hz;
+    o.squelch_level = f->b200_cfg.squelch_level;
+    o.squelch_snr_db = f->b200_cfg.squelch_snr_db;
+    o.lowpass_hz = f->b200_cfg.lowpass_hz;
+    o.notch_hz = f->b200_cfg.notch_hz;
+    o.notch_q = f->b200_cfg.notch_q;
+    o.ctcss_hz = f->b200_cfg.ctcss_hz;
     o.afc = ch->afc;
+}
+
+// ---- mixers summed on the GPU -------------------------------------------------------------------------------------------
+namespace {
+struct GpuMixer {
+    mixer_t* mixer;  // the reference's object; its channel receives the sums
+};
+std::vector<GpuMixer> g_gpu_mixers;  // engine mixer index -> mixer (one demod thread owns a mixer entirely, or it stays on the CPU path)
+}  // namespace
+
+// process_outputs() asks this before mixer_put_samples (output.cpp:533-535): inputs of a GPU-summed mixer are not put again
+extern "C" ABG_API int b200_mixer_is_gpu(const mixer_t* m) {
+    for (const GpuMixer& g : g_gpu_mixers)
+        if (g.mixer == m) return 1;
+    return 0;
+}
+
+// Mixers all of whose inputs are channels of devices[d0, d1): (dev, chan, ampfactor, balance) per input in input order.
+static int configure_gpu_mixers(abg_engine* eng, device_t* devices, int d0, int d1) {
+    g_gpu_mixers.clear();
+    mixer_t* mixers = bd::mixer_array();
+    const int nm = bd::mixer_n();
+    if (!mixers || nm <= 0) return ABG_OK;
+    std::vector<std::vector<abg_mixer_input>> found(nm);
+    std::vector<std::vector<int>> slot(nm);
+    for (int i = d0; i < d1; i++) {
+        device_t* dev = devices + i;
+        for (int c = 0; c < dev->channel_count; c++) {
+            channel_t* ch = dev->channels + c;
+            for (int k = 0; k < ch->output_count; k++) {
+                if (ch->outputs[k].type != O_MIXER || !ch->outputs[k].enabled) continue;
+                mixer_data* md = (mixer_data*)ch->outputs[k].data;
+                const int m = (int)(md->mixer - mixers);
+                if (m < 0 || m >= nm) continue;
+                const mixinput_t& in = md->mixer->inputs[md->input];
+                abg_mixer_input mi;
+                mi.dev = i - d0;
+                mi.chan = c;
+                mi.ampfactor = in.ampfactor;
+                // ampl = fminf(1, 1 - balance), ampr = fminf(1, 1 + balance) (mixer.cpp:82-83), inverted
+                mi.balance = in.ampl < 1.0f ? 1.0f - in.ampl : (in.ampr < 1.0f ? in.ampr - 1.0f : 0.0f);
+                found[m].push_back(mi);
+                slot[m].push_back(md->input);
+            }
+        }
+    }
+    std::vector<int32_t> offs(1, 0);
+    std::vector<abg_mixer_input> flat;
+    for (int m = 0; m < nm; m++) {
+        if (!mixers[m].enabled || (int)found[m].size() != mixers[m].input_count || found[m].empty()) continue;  // some input lives elsewhere
+        std::vector<int> order(found[m].size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return slot[m][a] < slot[m][b]; });  // mix in input order (mixer.cpp:189)
+        for (int k : order) flat.push_back(found[m][k]);
+        offs.push_back((int32_t)flat.size());
+        g_gpu_mixers.push_back(GpuMixer{mixers + m});
+    }
+    if (g_gpu_mixers.empty()) return ABG_OK;
+    return abg_mixers_configure(eng, (int)g_gpu_mixers.size(), offs.data(), flat.data());
+}
+
+// Producer side of the mixer hand-off (what mixer_thread does once all inputs are in, mixer.cpp:186-252).
+static bool deliver_mixers(abg_engine* eng, Signal* sig, int B, std::vector<float>& left, std::vector<float>& right) {
+    bool any = false;
+    left.resize(B);
+    right.resize(B);
+    for (size_t em = 0; em < g_gpu_mixers.size(); em++) {
+        mixer_t* mixer = g_gpu_mixers[em].mixer;
+        channel_t* channel = &mixer->channel;
+        for (;;) {
+            if (g_b200.wait_for_consumer && channel->state == CH_READY) break;  // offline pacing: the output thread has not taken the last one yet
+            int has_signal = 0;
+            int rc = abg_fetch_mixer_batch(eng, (int)em, left.data(), right.data(), &has_signal);
+            if (rc <= 0) break;
+            if (channel->state == CH_READY) mixer->output_overrun_count++;  // previous output not yet handled (mixer.cpp:163-170)
+            channel->state = CH_WORKING;
+            memcpy(channel->waveout, left.data(), sizeof(float) * B);
+            if (channel->mode == MM_STEREO) memcpy(channel->waveout_r, right.data(), sizeof(float) * B);
+            channel->axcindicate = has_signal ? SIGNAL : NO_SIGNAL;
+            channel->state = CH_READY;
+            sig->send();
+            any = true;
+            if (g_b200.wait_for_consumer) break;
+        }
+    }
+    return any;
 }
 
 extern "C" void* demodulate_b200(void* params) {
     demod_params_t* dp = (demod_params_t*)params;
     const int d0 = dp->device_start, d1 = dp->device_end, nd = d1 - d0;
-    device_t* devices = g_b200.devices;
-    const int B = g_b200.wave_rate / 8;  // WAVE_BATCH
+    device_t* devices = bd::devs();
+    const int B = bd::wave_rate() / 8;  // WAVE_BATCH
 
     // ---- engine set-up: init_demod() + top of demodulate() (:253-266,292-351) ----
     std::vector<abg_device_cfg> dcfg(nd);
@@ -99,9 +180,9 @@ extern "C" void* demodulate_b200(void* params) {
         dcfg[i].channels = ccfg[i].data();
     }
     abg_config cfg;
-    cfg.fft_size = (int32_t)g_b200.fft_size;
-    cfg.wave_rate = g_b200.wave_rate;
-    cfg.fm_demod = g_b200.fm_demod;
+    cfg.fft_size = (int32_t)bd::fft();
+    cfg.wave_rate = bd::wave_rate();
+    cfg.fm_demod = bd::fm_demod_algo();
     cfg.n_devices = nd;
     cfg.devices = dcfg.data();
     abg_options opt;
@@ -119,7 +200,7 @@ extern "C" void* demodulate_b200(void* params) {
     std::vector<unsigned char*> pinned_rings;
     for (int i = 0; i < nd; i++) {
         input_t* in = devices[d0 + i].input;
-        const size_t ring_bytes = in->buf_size + 2 * (size_t)in->bytes_per_sample * g_b200.fft_size;
+        const size_t ring_bytes = in->buf_size + 2 * (size_t)in->bytes_per_sample * bd::fft();
         if (abg_host_register(in->buffer, ring_bytes) == ABG_OK) pinned_rings.push_back(in->buffer);
     }
     struct Unpin {
@@ -147,17 +228,33 @@ extern "C" void* demodulate_b200(void* params) {
             scan_idx[i][c] = 0;
         }
     }
+    if (configure_gpu_mixers(eng, devices, d0, d1) != ABG_OK) {
+        fatal("abg_mixers_configure failed");
+        abg_destroy(eng);
+        return NULL;
+    }
+    // which freqlist[] entry each enqueued batch was demodulated with (the engine is pipelined: by delivery time
+    // controller_thread may have moved freq_idx on, and active_counter belongs to the entry that produced the audio, :645)
+    struct Enq {
+        int n;
+        std::vector<int> idx;
+    };
+    std::vector<std::deque<Enq>> enq(nd);
     g_b200.engine_ready = 1;
-    std::vector<float> wo, iq;
+    std::vector<float> wo, iq, mleft, mright;
     std::vector<char> axc;
     bool idle = false;  // the previous pass neither pushed, demodulated nor delivered anything
     while (true) {
-        if (g_b200.do_exit) {
+        if (bd::exit_flag()) {
             abg_destroy(eng);
+            g_gpu_mixers.clear();
             return NULL;
         }
-        if (g_b200.devices_running == 0 && idle) {  // :377-381 — but only once everything buffered has been delivered
-            g_b200.do_exit = 1;                         // log(LOG_ERR, "All receivers failed, exiting\n") in the reference tree
+        if (bd::running() == 0 && idle) {  // :377-381 — but only once everything buffered has been delivered
+#ifdef ABG_WITH_REFERENCE_HEADERS
+            log(LOG_ERR, "All receivers failed, exiting\n");
+#endif
+            bd::exit_flag() = 1;
             continue;
         }
         bool pushed = false;
@@ -175,7 +272,8 @@ extern "C" void* demodulate_b200(void* params) {
             if (in->state != INPUT_RUNNING) {  // :383-391
                 if (in->state == INPUT_FAILED) {
                     in->state = INPUT_DISABLED;
-                    g_b200.devices_running--;
+                    bd::device_failed(dev);  // disable_device_outputs(dev), :386
+                    bd::running()--;
                 }
                 // whatever is still buffered is demodulated (the reference also drains until `available` runs short)
             }
@@ -215,11 +313,17 @@ extern "C" void* demodulate_b200(void* params) {
                 scan_idx[i][c] = want;
             }
         }
+        std::vector<int> ready_before(nd);
+        for (int i = 0; i < nd; i++) ready_before[i] = abg_batches_ready(eng, i);
         int produced = abg_run(eng, -1);
         if (produced < 0 && produced != ABG_EOVERFLOW) {
             fatal("abg_run failed");
             abg_destroy(eng);
             return NULL;
+        }
+        for (int i = 0; i < nd; i++) {
+            const int n_new = abg_batches_ready(eng, i) - ready_before[i];
+            if (n_new > 0) enq[i].push_back(Enq{n_new, scan_idx[i]});
         }
         // (after abg_run, so that waiting for the copies overlaps the kernels that were just enqueued)
         if (pushed) {
@@ -247,13 +351,21 @@ extern "C" void* demodulate_b200(void* params) {
                     return NULL;
                 }
                 if (rc == 0) break;
+                const std::vector<int>* used = nullptr;
+                if (!enq[i].empty()) {
+                    used = &enq[i].front().idx;
+                }
                 for (int c = 0; c < C; c++) {
                     channel_t* ch = dev->channels + c;
                     memcpy(ch->waveout, wo.data() + (size_t)c * B, sizeof(float) * B);
                     if (ch->has_iq_outputs) memcpy(ch->iq_out, iq.data() + (size_t)c * 2 * B, sizeof(float) * 2 * B);
                     ch->axcindicate = (enum status)axc[c];
-                    if (ch->axcindicate != NO_SIGNAL) ch->freqlist[ch->freq_idx].active_counter++;  // :645-647
+                    if (ch->axcindicate != NO_SIGNAL) {  // :645-647
+                        const int fi = (used && (*used)[c] >= 0) ? (*used)[c] : ch->freq_idx;
+                        ch->freqlist[fi].active_counter++;
+                    }
                 }
+                if (!enq[i].empty() && --enq[i].front().n == 0) enq[i].pop_front();
                 if (dev->waveavail == 1)
                     dev->output_overrun_count++;  // :649-652
                 else
@@ -263,6 +375,7 @@ extern "C" void* demodulate_b200(void* params) {
                 if (g_b200.wait_for_consumer) break;
             }
         }
+        if (!g_gpu_mixers.empty() && deliver_mixers(eng, dp->mp3_signal, B, mleft, mright)) delivered = true;
         idle = !pushed && !delivered && produced <= 0;
         if (idle) {
             bool waiting = false;  // batches held back only because the output thread has not consumed the previous one
@@ -273,22 +386,31 @@ extern "C" void* demodulate_b200(void* params) {
     }
 }
 
-// refresh the Squelch getters of one channel for the stats file / TUI (output.cpp:606-766, rtl_airband.cpp:632-643)
+// refresh the Squelch read-outs of one device's channels for the stats file / TUI (output.cpp:598-869, rtl_airband.cpp:632-643)
 extern "C" ABG_API int b200_refresh_stats(abg_engine* eng, int dev_local, device_t* dev) {
     for (int c = 0; c < dev->channel_count; c++) {
         abg_squelch_stats s;
         int rc = abg_get_stats(eng, dev_local, c, &s);
         if (rc != ABG_OK) return rc;
         freq_t* f = dev->channels[c].freqlist + dev->channels[c].freq_idx;
-        f->noise_level = s.noise_level;
-        f->signal_level = s.signal_level;
-        f->squelch_level_now = s.squelch_level;
-        f->open_count = s.open_count;
-        f->flappy_count = s.flappy_count;
-        f->ctcss_count = s.ctcss_count;
-        f->no_ctcss_count = s.no_ctcss_count;
+        f->b200_stats.noise_level = s.noise_level;
+        f->b200_stats.signal_level = s.signal_level;
+        f->b200_stats.squelch_level = s.squelch_level;
+        f->b200_stats.noise_level_dbfs = s.noise_level_dbfs;
+        f->b200_stats.signal_level_dbfs = s.signal_level_dbfs;
+        f->b200_stats.squelch_level_dbfs = s.squelch_level_dbfs;
+        f->b200_stats.open_count = s.open_count;
+        f->b200_stats.flappy_count = s.flappy_count;
+        f->b200_stats.ctcss_count = s.ctcss_count;
+        f->b200_stats.no_ctcss_count = s.no_ctcss_count;
         f->agcavgfast = s.agcavgfast;
         dev->bins[c] = (size_t)s.bin;
     }
     return ABG_OK;
+}
+
+// output.cpp:519-522: buflen = 2 * sizeof(float) * WAVE_BATCH; fwrite(channel->iq_out, 1, buflen, f)
+extern "C" ABG_API size_t b200_write_rawfile(FILE* f, const channel_t* channel, int wave_batch) {
+    const size_t buflen = 2 * sizeof(float) * (size_t)wave_batch;
+    return fwrite(channel->iq_out, 1, buflen, f);
 }

@@ -13,9 +13,30 @@
 #include <cmath>
 #include <vector>
 
-#include "airband_host.h"
+#include "b200_adapter.h"
 
 #define MIN_BUF_SIZE 2560000  // reference src/rtl_airband.h:61
+
+// reference src/input-helpers.cpp:37-63, restated for the test feeders (the producer side is reference code; in the
+// reference tree its own definition is the one that links)
+void circbuffer_append(input_t* const input, unsigned char* buf, size_t len) {
+    if (len == 0) return;
+    pthread_mutex_lock(&input->buffer_lock);
+    const size_t tail = 2 * input->bytes_per_sample * g_b200.fft_size;
+    size_t space_left = input->buf_size - input->bufe;
+    if (space_left >= len) {
+        memcpy(input->buffer + input->bufe, buf, len);
+        if (input->bufe == 0) memcpy(input->buffer + input->buf_size, input->buffer, std::min(len, tail));
+    } else {
+        memcpy(input->buffer + input->bufe, buf, space_left);
+        memcpy(input->buffer, buf + space_left, len - space_left);
+        memcpy(input->buffer + input->buf_size, input->buffer, std::min(len - space_left, tail));
+    }
+    size_t old_end = input->bufe;
+    input->bufe = (input->bufe + len) % input->buf_size;
+    if (old_end < input->bufs && input->bufe >= input->bufs) input->overflow_count++;
+    pthread_mutex_unlock(&input->buffer_lock);
+}
 
 namespace {
 struct Feeder {
@@ -72,12 +93,46 @@ struct Harness {
     std::vector<int> n_batches;
     int B = 0, wave_len = 0;
     Signal sig;
+    // mixers (mixer_t + the O_MIXER outputs of the input channels, as parse_mixers()/parse_outputs() leave them)
+    std::vector<mixer_t> mixers;
+    std::vector<std::vector<mixinput_t>> mix_inputs;
+    std::vector<std::vector<float>> mix_wave, mix_wave_r;
+    std::vector<std::vector<std::vector<output_t>>> outputs;      // [dev][chan][k]
+    std::vector<std::vector<std::vector<mixer_data>>> mix_data;   // storage behind output_t.data
+    std::vector<std::vector<float>> out_mix_l, out_mix_r;        // per mixer: batches x B
+    std::vector<std::vector<char>> out_mix_axc;
+    std::vector<int> n_mix_batches;
+    std::vector<int> failed_calls;                                // disable_device_outputs stand-in: calls per device
+    // O_RAWFILE stand-in: (dev, chan) -> FILE*
+    struct Raw {
+        int dev, chan;
+        FILE* f;
+    };
+    std::vector<Raw> rawfiles;
 };
+Harness* g_harness = nullptr;
+void on_device_failed(device_t* dev) {
+    if (g_harness) g_harness->failed_calls[dev - g_harness->devs.data()]++;
+}
 struct Consumer {
     Harness* h;
     volatile int stop;
 };
 void consume_ready(Harness* h) {
+    // output_thread(): mixers first (output.cpp:888-896), then the devices (:903-923)
+    for (size_t m = 0; m < h->mixers.size(); m++) {
+        channel_t* channel = &h->mixers[m].channel;
+        if (!h->mixers[m].enabled || channel->state != CH_READY) continue;
+        h->out_mix_l[m].insert(h->out_mix_l[m].end(), channel->waveout, channel->waveout + h->B);
+        h->out_mix_r[m].insert(h->out_mix_r[m].end(), channel->waveout_r, channel->waveout_r + h->B);
+        h->out_mix_axc[m].push_back((char)channel->axcindicate);
+        h->n_mix_batches[m]++;
+        channel->state = CH_DIRTY;
+    }
+    for (const Harness::Raw& r : h->rawfiles) {  // process_outputs(), O_RAWFILE branch (output.cpp:519-522)
+        device_t* dev = &h->devs[r.dev];
+        if (dev->waveavail) b200_write_rawfile(r.f, dev->channels + r.chan, h->B);
+    }
     for (size_t i = 0; i < h->devs.size(); i++) {
         device_t* dev = &h->devs[i];
         if (!dev->waveavail) continue;
@@ -157,8 +212,7 @@ ABG_API void* abh_create(const abg_config* cfg, int max_batches_per_run) {
             f.agcavgfast = 0.5f;
             f.ampfactor = cc.ampfactor;
             f.modulation = cc.modulation == ABG_MOD_NFM ? MOD_NFM : MOD_AM;
-            f.squelch_level = cc.squelch_level; f.squelch_snr_db = cc.squelch_snr_db; f.notch_hz = cc.notch_hz; f.notch_q = cc.notch_q;
-            f.ctcss_hz = cc.ctcss_hz; f.lowpass_hz = cc.lowpass_hz;
+            f.b200_cfg = b200_freq_cfg{cc.squelch_level, cc.squelch_snr_db, cc.notch_hz, cc.notch_q, cc.ctcss_hz, cc.lowpass_hz};
             h->bins[i][c] = h->base_bins[i][c] = (size_t)cc.bin;
         }
         device_t& d = h->devs[i];
@@ -172,7 +226,87 @@ ABG_API void* abh_create(const abg_config* cfg, int max_batches_per_run) {
     g_b200.devices = h->devs.data();
     g_b200.device_count = D;
     g_b200.devices_running = D;
+    h->failed_calls.assign(D, 0);
+    h->outputs.resize(D);
+    h->mix_data.resize(D);
+    for (int i = 0; i < D; i++) {
+        h->outputs[i].resize(h->chans[i].size());
+        h->mix_data[i].resize(h->chans[i].size());
+    }
+    g_harness = h;
+    g_b200.on_device_failed = on_device_failed;
     return h;
+}
+
+// mixers as parse_mixers() + mixer_connect_input() leave them (mixer.cpp:55-96): mixer m owns inputs
+// [offsets[m], offsets[m+1]); every input is an O_MIXER output of its channel.  Call before abh_run.
+ABG_API int abh_set_mixers(void* hp, int n_mixers, const int32_t* offsets, const abg_mixer_input* inputs) {
+    Harness* h = (Harness*)hp;
+    h->mixers.resize(n_mixers);
+    h->mix_inputs.resize(n_mixers);
+    h->mix_wave.resize(n_mixers); h->mix_wave_r.resize(n_mixers);
+    h->out_mix_l.resize(n_mixers); h->out_mix_r.resize(n_mixers); h->out_mix_axc.resize(n_mixers);
+    h->n_mix_batches.assign(n_mixers, 0);
+    // reserve the per-channel output arrays first: output_t.data points into mix_data
+    std::vector<std::vector<int>> count(h->devs.size());
+    for (size_t i = 0; i < h->devs.size(); i++) count[i].assign(h->chans[i].size(), 0);
+    for (int k = 0; k < offsets[n_mixers]; k++) {
+        if (inputs[k].dev < 0 || inputs[k].dev >= (int)h->devs.size() || inputs[k].chan < 0 || inputs[k].chan >= h->devs[inputs[k].dev].channel_count) return -1;
+        count[inputs[k].dev][inputs[k].chan]++;
+    }
+    for (size_t i = 0; i < h->devs.size(); i++)
+        for (size_t c = 0; c < h->chans[i].size(); c++) {
+            h->outputs[i][c].clear(); h->outputs[i][c].reserve(count[i][c]);
+            h->mix_data[i][c].clear(); h->mix_data[i][c].reserve(count[i][c]);
+        }
+    for (int m = 0; m < n_mixers; m++) {
+        mixer_t& mx = h->mixers[m];
+        memset(&mx, 0, sizeof(mx));
+        mx.name = "mixer";
+        mx.enabled = true;
+        mx.interval = 2;  // MIX_DIVISOR
+        const int n_in = offsets[m + 1] - offsets[m];
+        h->mix_inputs[m].assign(n_in, mixinput_t{});
+        h->mix_wave[m].assign(h->wave_len, 0.0f);
+        h->mix_wave_r[m].assign(h->wave_len, 0.0f);
+        mx.channel.waveout = h->mix_wave[m].data();
+        mx.channel.waveout_r = h->mix_wave_r[m].data();
+        mx.channel.mode = MM_MONO;
+        mx.channel.state = CH_DIRTY;
+        mx.channel.axcindicate = NO_SIGNAL;
+        for (int j = 0; j < n_in; j++) {
+            const abg_mixer_input& in = inputs[offsets[m] + j];
+            mixinput_t& mi = h->mix_inputs[m][j];
+            mi.ampfactor = in.ampfactor;
+            mi.ampl = fminf(1.0f, 1.0f - in.balance);  // mixer_connect_input(), mixer.cpp:82-83
+            mi.ampr = fminf(1.0f, 1.0f + in.balance);
+            if (in.balance != 0.0f) mx.channel.mode = MM_STEREO;
+            h->mix_data[in.dev][in.chan].push_back(mixer_data{&mx, j});
+            output_t o;
+            o.type = O_MIXER; o.enabled = true; o.active = false; o.data = &h->mix_data[in.dev][in.chan].back();
+            h->outputs[in.dev][in.chan].push_back(o);
+        }
+        mx.input_count = n_in;
+        mx.inputs = h->mix_inputs[m].data();
+    }
+    for (size_t i = 0; i < h->devs.size(); i++)
+        for (size_t c = 0; c < h->chans[i].size(); c++) {
+            h->chans[i][c].output_count = (int)h->outputs[i][c].size();
+            h->chans[i][c].outputs = h->outputs[i][c].data();
+        }
+    g_b200.mixers = h->mixers.data();
+    g_b200.mixer_count = n_mixers;
+    return 0;
+}
+
+// O_RAWFILE stand-in: every delivered batch of devices[dev].channels[chan] is appended to `path` the way process_outputs()
+// writes a .cf32 file (output.cpp:519-522).  Call before abh_run; the file is closed by abh_destroy.
+ABG_API int abh_add_rawfile(void* hp, int dev, int chan, const char* path) {
+    Harness* h = (Harness*)hp;
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    h->rawfiles.push_back(Harness::Raw{dev, chan, f});
+    return 0;
 }
 
 // scan mode: give devices[dev].channels[chan] a frequency list (freq_t part of every entry from freqs[]) and the entry
@@ -189,8 +323,7 @@ ABG_API int abh_set_freqlist(void* hp, int dev, int chan, int n_freqs, const abg
         f.agcavgfast = 0.5f;
         f.ampfactor = cc.ampfactor;
         f.modulation = cc.modulation == ABG_MOD_NFM ? MOD_NFM : MOD_AM;
-        f.squelch_level = cc.squelch_level; f.squelch_snr_db = cc.squelch_snr_db; f.notch_hz = cc.notch_hz; f.notch_q = cc.notch_q;
-        f.ctcss_hz = cc.ctcss_hz; f.lowpass_hz = cc.lowpass_hz;
+        f.b200_cfg = b200_freq_cfg{cc.squelch_level, cc.squelch_snr_db, cc.notch_hz, cc.notch_q, cc.ctcss_hz, cc.lowpass_hz};
     }
     channel_t& ch = h->chans[dev][chan];
     ch.freqlist = list.data();
@@ -362,6 +495,21 @@ ABG_API size_t abh_active_counter(void* hp, int dev, int chan) {
     return ch.freqlist[ch.freq_idx].active_counter;
 }
 ABG_API const char* abh_last_error(void) { return g_b200.last_error; }
-ABG_API void abh_destroy(void* hp) { delete (Harness*)hp; }
+ABG_API int abh_mixer_batches(void* hp, int m) { return ((Harness*)hp)->n_mix_batches[m]; }
+ABG_API const float* abh_mixer_left(void* hp, int m) { return ((Harness*)hp)->out_mix_l[m].data(); }
+ABG_API const float* abh_mixer_right(void* hp, int m) { return ((Harness*)hp)->out_mix_r[m].data(); }
+ABG_API const char* abh_mixer_axc(void* hp, int m) { return ((Harness*)hp)->out_mix_axc[m].data(); }
+ABG_API size_t abh_mixer_overruns(void* hp, int m) { return ((Harness*)hp)->mixers[m].output_overrun_count; }
+ABG_API int abh_mixer_is_gpu(void* hp, int m) { return b200_mixer_is_gpu(&((Harness*)hp)->mixers[m]); }
+ABG_API int abh_failed_calls(void* hp, int dev) { return ((Harness*)hp)->failed_calls[dev]; }
+ABG_API void abh_destroy(void* hp) {
+    Harness* h = (Harness*)hp;
+    for (auto& r : h->rawfiles)
+        if (r.f) fclose(r.f);
+    if (g_harness == h) g_harness = nullptr;
+    g_b200.mixers = nullptr;
+    g_b200.mixer_count = 0;
+    delete h;
+}
 
 }  // extern "C"

@@ -9,7 +9,7 @@
 
 #include <algorithm>
 
-#include "airband_host.h"
+#include "b200_adapter.h"
 
 namespace {
 double now_s() {

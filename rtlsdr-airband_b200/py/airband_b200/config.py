@@ -83,6 +83,10 @@ class CSquelchStats(C.Structure):
         ("dm_phi", C.c_uint32),
         ("bin", C.c_int32),
         ("active_counter", C.c_uint64),
+        # level_to_dBFS() of the three levels, util.cpp:169-180
+        ("noise_level_dbfs", C.c_float),
+        ("signal_level_dbfs", C.c_float),
+        ("squelch_level_dbfs", C.c_float),
     ]
 
 
