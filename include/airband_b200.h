@@ -225,6 +225,11 @@ ABG_API int abg_mixer_device_buffers(abg_engine* e, float** dev_sums, int32_t** 
 /* Run conversion + window + FFT on one frame of `dev`'s format and return the full spectrum in natural bin order
  * (fftout[2*fft_size]); exercises the same kernel code as abg_run. */
 ABG_API int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout);
+/* Feed |X[bin]| values straight into the demodulation state machine of one device (K1 skipped): wavein[C][n_batches *
+ * WAVE_BATCH] becomes channel_t.wavein[AGC_EXTRA ...]; results are fetched as usual.  For the ports of the reference's own
+ * Squelch / CTCSS unit tests (reference src/test_squelch.cpp:51-281, src/test_ctcss.cpp:122-155).  The device must not be
+ * fed with abg_push and its channels must not need raw I/Q or AFC.  Returns the number of batches enqueued. */
+ABG_API int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const float* wavein);
 /* Host-only: plan and coefficient table of the tensor-core K1 (fft_mode 3) for one device, as abg_create builds them
  * (window * twiddle quantised to `digits` signed 8-bit digits, in the shared-memory image the MMA reads).
  * plan[12] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo}; tab == NULL queries the plan only. */

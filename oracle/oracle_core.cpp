@@ -515,6 +515,24 @@ long abo_run(void* h, int max_batches, int n_threads) {
     return total;
 }
 
+// stage tap (mirrors abg_debug_inject_wavein): wavein[C][n_batches * B] becomes channel_t.wavein[AGC_EXTRA ...], batch by batch
+int abo_debug_inject_wavein(void* h, int dev, int n_batches, const float* wavein) {
+    Oracle* o = (Oracle*)h;
+    if (dev < 0 || dev >= o->ndev() || n_batches < 1 || !wavein) return -1;
+    Device& d = o->D(dev);
+    const int B = o->wave_batch;
+    for (auto& cp : d.ch)
+        if (cp->needs_raw_iq || cp->afc) return -1;
+    if (d.waveend != 0 && d.waveend != AGC_EXTRA) return -1;  // mixing injection with real frames is not supported
+    for (int b = 0; b < n_batches; b++) {
+        for (size_t c = 0; c < d.ch.size(); c++)
+            memcpy(d.ch[c]->wavein.data() + AGC_EXTRA, wavein + (c * (size_t)n_batches + b) * B, sizeof(float) * B);
+        d.waveend = B + AGC_EXTRA;
+        demod_batch(*o, d, nullptr);
+    }
+    return n_batches;
+}
+
 void abo_set_discard(void* h, int discard) { ((Oracle*)h)->discard = discard != 0; }
 void abo_set_pin(void* h, const int* cpus, int n) {
     Oracle* o = (Oracle*)h;

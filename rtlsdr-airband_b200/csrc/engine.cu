@@ -780,7 +780,7 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
 }
 
 // enqueue K1 (+K2) for the per-device batch counts in nb[]; `resident` selects the replay buffers.
-int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool queue_outputs, int* n_enqueued) {
+int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool queue_outputs, int* n_enqueued, bool skip_k1 = false) {
     const int B = e->B, N = e->N;
     int total = 0, nbrun = 0;
     for (int v : nb) {
@@ -793,7 +793,8 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     if (queue_outputs) {
         slot = e->next_slot;
         if (e->slots[slot].pending > 0 || e->slots[slot].mix_pending > 0)
-            return fail(ABG_EOVERFLOW, "output overrun: %d finished batches not fetched yet", e->slots[slot].pending + e->slots[slot].mix_pending);
+            return fail(ABG_EOVERFLOW, "output overrun: %d finished device batches and %d mixer batches of an earlier run not fetched yet (every configured mixer has to be drained with abg_fetch_mixer_batch)",
+                        e->slots[slot].pending, e->slots[slot].mix_pending);
         e->next_slot = (e->next_slot + 1) % (int)e->slots.size();
     }
     cudaStream_t sa = e->stream, sb = e->stream_b;
@@ -812,6 +813,7 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     CU(cudaEventRecord(tl[0], sa));
     // ---- K1 per group (stream A) ----
     for (auto& g : e->groups) {
+        if (skip_k1) break;  // abg_debug_inject_wavein: the magnitudes were written into win[cur] directly
         int max_frames = 0;
         for (size_t k = 0; k < g.devs.size(); k++) {
             const int di = g.devs[k];
@@ -924,7 +926,9 @@ int enqueue_run(abg_engine* e, const std::vector<int>& nb, bool resident, bool q
     for (size_t i = 0; i < e->dev.size(); i++) {
         if (nb[i] <= 0) continue;
         Device& d = e->dev[i];
-        if (resident) {
+        if (skip_k1) {
+            // nothing was consumed from the raw stream
+        } else if (resident) {
             d.res_primed = true;
         } else {
             const int frames = nb[i] * B + (d.primed ? 0 : ABG_AGC_EXTRA);
@@ -1030,10 +1034,9 @@ int abg_run(abg_engine* e, int max_batches) {
     if (max_batches < 0 || max_batches > e->nbmax) max_batches = e->nbmax;
     // AFC moves bins[] between batches (rtl_airband.cpp:629): with any AFC channel the run advances one batch at a
     // time so that K1 of batch k+1 sees the bins K2 chose at the end of batch k.
-    for (auto& d : e->dev)
-        if (d.has_afc) max_batches = 1;
+    // (only the AFC devices: the others still advance by up to max_batches in the same run)
     std::vector<int> nb(e->dev.size());
-    for (size_t i = 0; i < e->dev.size(); i++) nb[i] = std::min(max_batches, abg_batches_available(e, (int)i));
+    for (size_t i = 0; i < e->dev.size(); i++) nb[i] = std::min(e->dev[i].has_afc ? 1 : max_batches, abg_batches_available(e, (int)i));
     int n = 0;
     int rc = enqueue_run(e, nb, false, true, &n);
     return rc != ABG_OK ? rc : n;
@@ -1426,6 +1429,35 @@ int abg_debug_tc_table(int fft_size, int sfmt, int hop_bytes, float fullscale, i
     for (auto& w : wsc) w = w * scale;
     abg_k1tc_build_table(p, fft_size, sfmt, wsc.data(), bins, n_channels, tab, sq, cscale);
     return ABG_OK;
+}
+
+// Stage tap for the upstream squelch / CTCSS behavioural tests (reference src/test_squelch.cpp, src/test_ctcss.cpp): feed
+// |X[bin]| values straight into the demodulation state machine.  wavein[C][n_batches * WAVE_BATCH] becomes
+// channel_t.wavein[AGC_EXTRA ...] of the device's channels (the AGC look-back keeps its initial 20.0, config.cpp:313-316, on
+// the first call and the previous tail afterwards), K1 is skipped, K2 runs n_batches batches, results are fetched as usual.
+// A device driven this way must not be fed with abg_push, and its channels must not need raw I/Q or AFC.
+int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const float* wavein) {
+    if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_debug_inject_wavein: device %d out of range", dev);
+    if (n_batches < 1 || n_batches > e->nbmax || !wavein) return fail(ABG_EINVAL, "abg_debug_inject_wavein: n_batches must be 1..%d", e->nbmax);
+    Device& d = e->dev[dev];
+    for (int c = 0; c < d.C; c++)
+        if (e->h_params[d.g0 + c].needs_raw_iq || e->h_params[d.g0 + c].afc) return fail(ABG_EINVAL, "abg_debug_inject_wavein: channel %d needs raw I/Q or AFC", c);
+    cudaSetDevice(e->cuda_dev);
+    CU(cudaStreamSynchronize(e->stream_c));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->stream_b));
+    const int B = e->B, cur = (int)(e->run_index & 1);
+    const size_t rows = (size_t)n_batches * B;
+    std::vector<float> tm(rows * d.C);  // time-major like win[][]
+    for (int c = 0; c < d.C; c++)
+        for (size_t r = 0; r < rows; r++) tm[r * d.C + c] = wavein[(size_t)c * rows + r];
+    CU(cudaMemcpy2D(e->win[cur].p + (size_t)ABG_AGC_EXTRA * e->Gp + d.g0, sizeof(float) * e->Gp, tm.data(), sizeof(float) * d.C, sizeof(float) * d.C, rows,
+                    cudaMemcpyHostToDevice));
+    std::vector<int> nb(e->dev.size(), 0);
+    nb[dev] = n_batches;
+    int n = 0;
+    int rc = enqueue_run(e, nb, false, true, &n, true);
+    return rc != ABG_OK ? rc : n;
 }
 
 int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout) {

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "../../include/airband_b200.h"
+#include "../../include/airband_b200_host.h"
 
 #define AGC_EXTRA 100  // reference src/rtl_airband.h:74
 
@@ -75,19 +76,7 @@ class Signal {  // rtl_airband.h:201-221
     pthread_mutex_t mutex_;
 };
 
-// What the WITH_B200 patch adds to the reference's freq_t (integration/reference_b200.patch): the values parse_channels()
-// hands to Squelch / NotchFilter / LowpassFilter (config.cpp:437-619; those objects have no getters), and the
-// Squelch read-outs the stats file / TUI use (squelch.h:89-96, output.cpp:598-869, rtl_airband.cpp:632-643), refreshed from
-// the engine by b200_refresh_stats().
-struct b200_freq_cfg {
-    float squelch_level, squelch_snr_db, notch_hz, notch_q, ctcss_hz, lowpass_hz;
-};
-struct b200_freq_stats {
-    float noise_level, signal_level, squelch_level;
-    float noise_level_dbfs, signal_level_dbfs, squelch_level_dbfs;  // level_to_dBFS(), util.cpp:178-180
-    size_t open_count, flappy_count, ctcss_count, no_ctcss_count;
-};
-
+// b200_freq_cfg / b200_freq_stats: what the WITH_B200 patch adds to the reference's freq_t (include/airband_b200_host.h)
 struct freq_t {
     int frequency;
     float agcavgfast;  // mirrored back from the engine for the stats file

@@ -22,7 +22,7 @@ SYMBOLS = [
     "abg_last_error", "abg_version", "abg_create", "abg_destroy", "abg_wave_batch", "abg_hop", "abg_push",
     "abg_batches_available", "abg_run", "abg_sync", "abg_join", "abg_batches_ready", "abg_fetch_batch", "abg_fetch_batches", "abg_get_stats", "abg_set_bin",
     "abg_resident_load", "abg_run_resident", "abg_set_stream", "abg_launch_count", "abg_mixers_configure",
-    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline", "abg_scan_configure", "abg_scan_select", "abg_host_register", "abg_host_unregister", "abg_ingest_sync", "abg_fft_path", "abg_debug_tc_table",
+    "abg_fetch_mixer_batch", "abg_mixer_device_buffers", "abg_debug_frame", "abg_last_run_times", "abg_debug_timeline", "abg_scan_configure", "abg_scan_select", "abg_host_register", "abg_host_unregister", "abg_ingest_sync", "abg_fft_path", "abg_debug_tc_table", "abg_debug_inject_wavein",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
     L.abg_scan_select.restype, L.abg_scan_select.argtypes = i, [vp, i, i, i]
     L.abg_debug_timeline.restype, L.abg_debug_timeline.argtypes = i, [vp, i, C.POINTER(C.c_float)]
     L.abg_fft_path.restype, L.abg_fft_path.argtypes = i, [vp, i]
+    L.abg_debug_inject_wavein.restype, L.abg_debug_inject_wavein.argtypes = i, [vp, i, i, vp]
     L.abg_debug_tc_table.restype = i
     L.abg_debug_tc_table.argtypes = [i, i, i, f, i, vp, i, vp, vp, C.c_size_t, vp, C.POINTER(C.c_double)]
     _LIB = L
@@ -262,6 +263,12 @@ class Engine:
         a, b = C.c_void_p(), C.c_void_p()
         self._chk(self.L.abg_mixer_device_buffers(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def inject_wavein(self, dev: int, wavein: np.ndarray) -> int:
+        """Stage tap: wavein[C, n_batches * B] straight into the demodulation state machine (K1 skipped)."""
+        w = np.ascontiguousarray(wavein, np.float32)
+        assert w.ndim == 2 and w.shape[1] % self.B == 0
+        return self._chk(self.L.abg_debug_inject_wavein(self.h, dev, w.shape[1] // self.B, _ptr(w)))
 
     # ---- stage tap ------------------------------------------------------------------------------------------------
     def debug_frame(self, dev: int, raw_frame: np.ndarray) -> np.ndarray:
