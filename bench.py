@@ -297,6 +297,13 @@ def cpu_run(cfg, desc, steps: int, warmup: int, budget_s: float = 20.0, extras: 
                       f"each pinned to its own physical core; oracle variant {variant} (-O3 -ffast-math, x86-64-v3); FFTW is not installable offline: "
                       f"own scalar radix-4 FP32 FFT, which understates FFTW's SIMD codelets by an unmeasured factor",
             "best_step_value": best, "cpu_model": cpu["model"], "physical_cores": cpu["physical_cores"], "logical_cpus": cpu["logical_cpus"]}
+    try:
+        sec = op.lib(variant).abo_fft_seconds(cfg.fft_size, 4000)
+        info["fft"] = {"us_per_transform": sec * 1e6, "nominal_gflops": 5 * cfg.fft_size * math.log2(cfg.fft_size) / sec / 1e9,
+                       "note": "the oracle's own FP32 FFT alone, one core, persistent plan; FFTW's AVX2 codelets reach roughly 20-30 GFLOP/s per core at "
+                               "these sizes, so the FFT share of the CPU arm is within about 2x of what the reference would get from fftw3f"}
+    except Exception:
+        pass
     if extras:
         try:  # the reference's default: ONE demod thread round-robin over all devices (rtl_airband.cpp:1070-1086)
             os.sched_setaffinity(0, {pin[0]}) if pin else None

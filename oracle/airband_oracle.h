@@ -107,6 +107,7 @@ float abo_fast_atan2(float y, float x);                 /* rtl_airband.cpp:147-1
 float abo_polar_disc_fast(float ar, float aj, float br, float bj);
 float abo_fm_quadri_demod(float ar, float aj, float br, float bj);
 void abo_fft(int n, const float* in, float* out);
+double abo_fft_seconds(int n, int reps); /* seconds per n-point transform, persistent plan (CPU baseline self-description) */
 
 /* ---- per-sample leaf harness (ports of reference src/test_squelch.cpp / test_ctcss.cpp use these) ------ */
 void* abo_sq_new(void);

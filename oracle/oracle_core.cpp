@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -653,6 +654,21 @@ void abo_sincosf_lut(uint32_t phi, float* s, float* c) { g_lut.get(phi, s, c); }
 float abo_fast_atan2(float y, float x) { return fast_atan2(y, x); }
 float abo_polar_disc_fast(float ar, float aj, float br, float bj) { return polar_disc_fast(ar, aj, br, bj); }
 float abo_fm_quadri_demod(float ar, float aj, float br, float bj) { return fm_quadri_demod(ar, aj, br, bj); }
+// seconds per transform of the oracle's FFT stand-in with a persistent plan (what the demod loop pays per frame); lets the
+// CPU baseline say how far its FFT is from FFTW-class throughput on the box it ran on
+double abo_fft_seconds(int n, int reps) {
+    abo::Fft32 f(n);
+    std::vector<float> a(2 * (size_t)n), b(2 * (size_t)n);
+    for (size_t i = 0; i < a.size(); i++) a[i] = (float)((i * 7919u) % 1000u) / 1000.0f - 0.5f;
+    for (int i = 0; i < 16; i++) f.forward(a.data(), b.data());
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < reps; i++) f.forward(a.data(), b.data());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    volatile float sink = b[1];
+    (void)sink;
+    return ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)) / (reps > 0 ? reps : 1);
+}
 void abo_fft(int n, const float* in, float* out) {
     abo::Fft32 f(n);
     f.forward(in, out);

@@ -81,6 +81,7 @@ def lib(variant: str = "restated"):
         "abo_polar_disc_fast": (f, [f, f, f, f]),
         "abo_fm_quadri_demod": (f, [f, f, f, f]),
         "abo_fft": (None, [i, vp, vp]),
+        "abo_fft_seconds": (C.c_double, [i, i]),
         "abo_sq_new": (vp, []),
         "abo_sq_free": (None, [vp]),
         "abo_sq_set_level": (None, [vp, f]),
