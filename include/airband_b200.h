@@ -232,7 +232,7 @@ ABG_API int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float*
 ABG_API int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const float* wavein);
 /* Host-only: plan and coefficient table of the tensor-core K1 (fft_mode 3) for one device, as abg_create builds them
  * (window * twiddle quantised to `digits` signed 8-bit digits, in the shared-memory image the MMA reads).
- * plan[12] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo}; tab == NULL queries the plan only. */
+ * plan[13] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo, nacc}; tab == NULL queries the plan only. */
 ABG_API int abg_debug_tc_table(int fft_size, int sfmt, int hop_bytes, float fullscale, int n_channels, const int32_t* bins, int digits,
                                int32_t* plan, signed char* tab, size_t tab_cap, long long* sq, double* cscale);
 

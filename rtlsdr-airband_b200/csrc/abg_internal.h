@@ -142,7 +142,7 @@ int abg_k1p_tile_frames(int fft_size, int sfmt, int hop_bytes, int max_channels,
 // tensor-core variant (k1_tc.cu): the bins' DFT as an integer GEMM on tcgen05 (8-bit formats, hop_bytes % 32 == 0)
 struct K1TcPlan {
     int eligible;
-    int K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo;
+    int K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo, nacc;
     size_t table_bytes;
 };
 struct K1TcTables {

@@ -1413,13 +1413,13 @@ int abg_mixer_device_buffers(abg_engine* e, float** dev_sums, int32_t** dev_flag
 }
 
 // Host-only (no device needed): the tensor-core K1's plan and coefficient table for one device, exactly as abg_create
-// builds them.  plan[12] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo}.  tab may be null to
+// builds them.  plan[13] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo, nacc}.  tab may be null to
 // query the plan; otherwise tab_cap >= K*NC bytes and sq has C2p entries.
 int abg_debug_tc_table(int fft_size, int sfmt, int hop_bytes, float fullscale, int n_channels, const int32_t* bins, int digits, int32_t* plan,
                        signed char* tab, size_t tab_cap, long long* sq, double* cscale) {
     K1TcPlan p;
     abg_k1tc_plan(fft_size, sfmt, hop_bytes, n_channels, digits, &p);
-    const int32_t v[12] = {p.eligible, p.K, p.HC, p.S, p.NC, p.ND, p.C2p, p.KBS, p.NSTB, p.tmem_cols, p.smem_bytes, p.halo};
+    const int32_t v[13] = {p.eligible, p.K, p.HC, p.S, p.NC, p.ND, p.C2p, p.KBS, p.NSTB, p.tmem_cols, p.smem_bytes, p.halo, p.nacc};
     if (plan) memcpy(plan, v, sizeof(v));
     if (!p.eligible) return fail(ABG_EINVAL, "abg_debug_tc_table: configuration not eligible for the tensor-core K1");
     if (!tab) return ABG_OK;

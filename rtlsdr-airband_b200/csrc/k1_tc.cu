@@ -83,8 +83,12 @@ struct Ctrl {
 static_assert(sizeof(Ctrl) <= TC_CTRL_BYTES, "control block too large");
 
 // Every wait below is mbar_wait_spin: bounded inside one asm statement, traps instead of hanging (tc_ptx.cuh).
-template <int TMEM_COLS, int KBS>
+// NACC independent partial accumulators per tile: consecutive MMAs into ONE accumulator serialise on the read-modify-write
+// of TMEM (measured: ~130 cycles per 128x64x32 MMA, 4x its issue time), so k-step k accumulates into partial k % NACC and the
+// epilogue adds the partials (integer sums are exact and commute).
+template <int NACC, int KBS>
 __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
+    constexpr int TMEM_COLS = 512;  // the whole tensor memory of the SM: 2 tiles x NACC partials x NCS columns
     extern __shared__ __align__(1024) unsigned char smem[];
     Ctrl* c = reinterpret_cast<Ctrl*>(smem);
     unsigned char* abuf = smem + TC_CTRL_BYTES;
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
     const int stage_bytes = KBS * a.NC * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int ACC_STRIDE = TMEM_COLS / 2;
+    constexpr int NCS = ACC_STRIDE / NACC;  // column stride between the partial accumulators of a tile (>= NC)
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
@@ -167,11 +172,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             for (int og = 0; og < a.C2p; og += 8) {
                 long long v[8];
                 for (int d = 0; d < a.ND; d++) {
-                    uint32_t rr[8];
-                    tmem_ld8(t0 + (uint32_t)(d * a.C2p + og), rr);
+                    uint32_t rr[NACC][8];
+#pragma unroll
+                    for (int pa = 0; pa < NACC; pa++) tmem_ld8(t0 + (uint32_t)(pa * NCS + d * a.C2p + og), rr[pa]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = (d == 0) ? (long long)(int32_t)rr[k] : (v[k] << 8) + (long long)(int32_t)rr[k];
+                    for (int k = 0; k < 8; k++) {
+                        int32_t sum = (int32_t)rr[0][k];
+#pragma unroll
+                        for (int pa = 1; pa < NACC; pa++) sum += (int32_t)rr[pa][k];  // the full sum fits S32 (|sum| <= 2N * 255 * 128)
+                        v[k] = (d == 0) ? (long long)sum : (v[k] << 8) + (long long)sum;
+                    }
                 }
                 float x[8];
 #pragma unroll
@@ -269,6 +280,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
         const uint32_t fb_bar0 = smem_u32(&c->full_b[0]), eb_bar0 = smem_u32(&c->empty_b[0]);
         uint32_t fb_bar = fb_bar0, eb_bar = eb_bar0;
         const uint32_t a_step = 2u * ((uint32_t)a.S >> 4);
+        // k-step number kbi * KBS + ks of the tile goes to partial accumulator (kbi * KBS + ks) % NACC; the first NACC k-steps
+        // overwrite (accumulate = 0)
+        auto acc_col = [](int kbi, int ks) -> uint32_t { return (uint32_t)(((kbi * KBS + ks) & (NACC - 1)) * NCS); };
+        auto acc_first = [](int kbi, int ks) -> bool { return kbi * KBS + ks < NACC; };
         for (int it = 0;; ++it) {
             const int slot = it & (TC_INFO_SLOTS - 1);
             mbar_wait_spin(smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1);
@@ -289,7 +304,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
                     const uint32_t base = a_lo + a.aoff[ksg];
                     if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < KBS; ks++) mma_i8_split(d_tmem, base + ks * a_step, a_hi, b_lo + ks * bstep16, b_hi, idesc, (kbi | ks) ? 1u : 0u);
+                        for (int ks = 0; ks < KBS; ks++)
+                            mma_i8_split(d_tmem + acc_col(kbi, ks), base + ks * a_step, a_hi, b_lo + ks * bstep16, b_hi, idesc, acc_first(kbi, ks) ? 0u : 1u);
                         mma_commit(eb_bar);
                     }
                 } else {
@@ -298,7 +314,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
                     for (int ks = 0; ks < KBS; ks++) ao[ks] = a_lo + a.aoff[ksg + ks];
                     if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < KBS; ks++) mma_i8_split(d_tmem, ao[ks], a_hi, b_lo + ks * bstep16, b_hi, idesc, (kbi | ks) ? 1u : 0u);
+                        for (int ks = 0; ks < KBS; ks++)
+                            mma_i8_split(d_tmem + acc_col(kbi, ks), ao[ks], a_hi, b_lo + ks * bstep16, b_hi, idesc, acc_first(kbi, ks) ? 0u : 1u);
                         mma_commit(eb_bar);
                     }
                 }
@@ -322,9 +339,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
     if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-template <int TMEM_COLS, int KBS>
+template <int NACC, int KBS>
 cudaError_t tc_launch_one(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
-    auto kern = k1_tc_kernel<TMEM_COLS, KBS>;
+    auto kern = k1_tc_kernel<NACC, KBS>;
     static AbgPerDeviceSize configured;  // per instantiation, per CUDA device
     cudaError_t e = configured.ensure(smem, [&]() {
         cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -336,13 +353,13 @@ cudaError_t tc_launch_one(const TcArgs& args, int grid, size_t smem, cudaStream_
     kern<<<grid, TC_THREADS, smem, s>>>(args);
     return cudaGetLastError();
 }
-template <int TMEM_COLS>
-cudaError_t tc_launch_cols(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
+template <int NACC>
+cudaError_t tc_launch_acc(const TcArgs& args, int grid, size_t smem, cudaStream_t s) {
     switch (args.KBS) {
-        case 1: return tc_launch_one<TMEM_COLS, 1>(args, grid, smem, s);
-        case 2: return tc_launch_one<TMEM_COLS, 2>(args, grid, smem, s);
-        case 4: return tc_launch_one<TMEM_COLS, 4>(args, grid, smem, s);
-        case 8: return tc_launch_one<TMEM_COLS, 8>(args, grid, smem, s);
+        case 1: return tc_launch_one<NACC, 1>(args, grid, smem, s);
+        case 2: return tc_launch_one<NACC, 2>(args, grid, smem, s);
+        case 4: return tc_launch_one<NACC, 4>(args, grid, smem, s);
+        case 8: return tc_launch_one<NACC, 8>(args, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -382,7 +399,11 @@ int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int d
     int cols = 32;
     while (cols < NC) cols <<= 1;
     p->eligible = 1; p->K = K; p->HC = HC; p->S = S; p->NC = NC; p->ND = digits; p->C2p = C2p; p->KBS = KBS; p->NSTB = nstb;
-    p->tmem_cols = 2 * cols; p->smem_bytes = (int)(base + (size_t)nstb * stage); p->halo = halo;
+    int nacc = 4;  // partial accumulators per tile: 2 tiles x nacc x cols <= 512 TMEM columns
+    while (nacc > 1 && 2 * nacc * cols > 512) nacc >>= 1;
+    if (const char* ev = getenv("ABG_K1_TC_NACC")) nacc = std::max(1, std::min(nacc, atoi(ev) >= 4 ? 4 : (atoi(ev) >= 2 ? 2 : 1)));
+    p->nacc = nacc;
+    p->tmem_cols = 512; p->smem_bytes = (int)(base + (size_t)nstb * stage); p->halo = halo;
     p->table_bytes = (size_t)K * NC;
     return 1;
 }
@@ -446,11 +467,10 @@ cudaError_t abg_launch_k1_tc(const K1Launch& L, const K1TcPlan& p, const K1TcTab
     if (const char* ev = getenv("ABG_K1_TC_ROTATE")) a.rotate = atoi(ev) != 0;
     if (a.total_tiles <= 0) return cudaSuccess;
     const int grid = std::min(a.total_tiles, std::max(sm_count, 1));
-    switch (p.tmem_cols) {
-        case 64: return tc_launch_cols<64>(a, grid, (size_t)p.smem_bytes, s);
-        case 128: return tc_launch_cols<128>(a, grid, (size_t)p.smem_bytes, s);
-        case 256: return tc_launch_cols<256>(a, grid, (size_t)p.smem_bytes, s);
-        case 512: return tc_launch_cols<512>(a, grid, (size_t)p.smem_bytes, s);
+    switch (p.nacc) {
+        case 1: return tc_launch_acc<1>(a, grid, (size_t)p.smem_bytes, s);
+        case 2: return tc_launch_acc<2>(a, grid, (size_t)p.smem_bytes, s);
+        case 4: return tc_launch_acc<4>(a, grid, (size_t)p.smem_bytes, s);
     }
     return cudaErrorInvalidValue;
 }

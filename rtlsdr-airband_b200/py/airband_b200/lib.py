@@ -278,14 +278,14 @@ class Engine:
         return out.view(np.complex64)
 
 
-TC_PLAN_FIELDS = ("eligible", "K", "HC", "S", "NC", "ND", "C2p", "KBS", "NSTB", "tmem_cols", "smem_bytes", "halo")
+TC_PLAN_FIELDS = ("eligible", "K", "HC", "S", "NC", "ND", "C2p", "KBS", "NSTB", "tmem_cols", "smem_bytes", "halo", "nacc")
 
 
 def tc_table(fft_size: int, sfmt: int, hop_bytes: int, bins: Sequence[int], digits: int = 4, fullscale: float = 1.0):
     """Host-only view of the tensor-core K1's plan and coefficient table (abg_debug_tc_table).  Returns (plan dict,
     tab int8[K/32, 2, NC, 16], sq int64[C2p], cscale) or (plan, None, None, None) when the shape is not eligible."""
     L = load()
-    plan = np.zeros(12, np.int32)
+    plan = np.zeros(13, np.int32)
     b = np.asarray(bins, np.int32)
     L.abg_debug_tc_table(fft_size, sfmt, hop_bytes, fullscale, len(b), _ptr(b), digits, _ptr(plan), None, 0, None, None)
     pd = dict(zip(TC_PLAN_FIELDS, (int(x) for x in plan)))
