@@ -230,6 +230,9 @@ ABG_API int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float*
  * Squelch / CTCSS unit tests (reference src/test_squelch.cpp:51-281, src/test_ctcss.cpp:122-155).  The device must not be
  * fed with abg_push and its channels must not need raw I/Q or AFC.  Returns the number of batches enqueued. */
 ABG_API int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const float* wavein);
+/* Measurement aid: per-role clock64 stamps of the tensor-core K1 (environment variable ABG_K1_TC_TRACE set at launch time);
+ * out[256 CTAs][4 roles: producer, epilogue, loader, MMA][16 tiles][4 events]. */
+ABG_API int abg_debug_k1tc_trace(long long* out);
 /* Host-only: plan and coefficient table of the tensor-core K1 (fft_mode 3) for one device, as abg_create builds them
  * (window * twiddle quantised to `digits` signed 8-bit digits, in the shared-memory image the MMA reads).
  * plan[13] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo, nacc}; tab == NULL queries the plan only. */

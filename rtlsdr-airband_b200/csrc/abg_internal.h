@@ -157,6 +157,7 @@ int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int d
 void abg_k1tc_build_table(const K1TcPlan& p, int fft_size, int sfmt, const float* wsc, const int32_t* bins, int n_channels, signed char* tab,
                           long long* sq, double* cscale);
 cudaError_t abg_launch_k1_tc(const K1Launch& L, const K1TcPlan& p, const K1TcTables& T, int sm_count, cudaStream_t s);
+int abg_k1tc_trace_dump(long long* out);  // measurement aid (ABG_K1_TC_TRACE): 256*4*16*4 clock64 stamps
 
 struct K2Launch {
     int G, Gp, P, wave_batch, fm_demod, iq_stride;  // iq_stride = nbmax * B

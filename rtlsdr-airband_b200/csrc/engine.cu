@@ -1460,6 +1460,10 @@ int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const float* 
     return rc != ABG_OK ? rc : n;
 }
 
+// measurement aid: clock64 stamps of the tensor-core K1's roles for the first 16 tiles of every CTA (set ABG_K1_TC_TRACE before
+// abg_create); out[256][4 roles][16 tiles][4 events]
+int abg_debug_k1tc_trace(long long* out) { return abg_k1tc_trace_dump(out) == 0 ? ABG_OK : fail(ABG_EINVAL, "no trace: ABG_K1_TC_TRACE was not set"); }
+
 int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout) {
     if (dev < 0 || dev >= (int)e->dev.size()) return fail(ABG_ERANGE, "abg_debug_frame: device %d out of range", dev);
     cudaSetDevice(e->cuda_dev);

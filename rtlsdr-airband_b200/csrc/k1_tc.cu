@@ -39,6 +39,7 @@
 
 namespace {
 using namespace tc;
+extern long long* g_tc_trace;
 
 constexpr int TC_THREADS = 320;
 constexpr int TC_CTRL_BYTES = 1024;
@@ -70,6 +71,8 @@ struct TcArgs {
     int mul, off;
     uint16_t aoff[512];        // per k-step start-address offset of the A operand, 16-byte units (K <= 16384)
     int stage_in_row;          // every B stage's k-steps lie inside one hop-row (HC/2 is a multiple of KBS)
+    long long* trace;          // measurement aid (ABG_K1_TC_TRACE): clock64 stamps [cta][role 0..3][tile 0..15][event 0..3], or null
+    int dbg_skip;              // measurement aid (ABG_K1_TC_SKIP): 1 = do not copy coefficients, 2 = do not copy samples, 4 = issue no MMA (results invalid)
     int rotate;                // start every CTA's K loop at a different coefficient block (exact integer sums commute)
 };
 
@@ -126,6 +129,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
     // block spreads the requests over the L2 slices (exact integer sums commute, so the K order is free).
     const int kb_rot = a.rotate ? (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)NKB) : 0;
 
+// stage-level stamps of tile 3: event e of stage st (< 16) goes to slot 32 + 2*st + e of the role's 64-slot block (tiles 8..15 unused then)
+#define TC_TRACE_STAGE(role, it, st, e)                                                                          \
+    do {                                                                                                         \
+        if (a.trace && (it) == 3 && (st) < 16 && (threadIdx.x & 31) == 0) a.trace[((size_t)blockIdx.x * 4 + (role)) * 64 + 32 + 2 * (st) + (e)] = clock64(); \
+    } while (0)
+#define TC_TRACE(role, it, ev)                                                                                   \
+    do {                                                                                                         \
+        if (a.trace && (it) < 8 && (threadIdx.x & 31) == 0) a.trace[(((size_t)blockIdx.x * 4 + (role)) * 16 + (it)) * 4 + (ev)] = clock64(); \
+    } while (0)
     if (warp < 4) {
         // ================= A producers =================
         for (int it = 0;; ++it) {
@@ -134,13 +146,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             const TileInfo ti = c->info[slot];
             if (ti.nf <= 0) break;
             const int buf = it & 1;
+            if (warp == 0) TC_TRACE(0, it, 0);
             mbar_wait_spin(smem_u32(&c->empty_a[buf]), ((it >> 1) & 1) ^ 1);
+            if (warp == 0) TC_TRACE(0, it, 1);
             const uint32_t dst0 = smem_u32(abuf + buf * abuf_bytes);
             const int total_chunks = ((ti.nf - 1) * a.hop_bytes + a.K) >> 4;
             int r = tid / a.HC, j = tid - r * a.HC;
             const int dr = 128 / a.HC, dj = 128 - dr * a.HC;
             for (int i = tid; i < total_chunks; i += 128) {
-                cp_async16(dst0 + j * a.S + r * 16, ti.src + (size_t)i * 16);
+                if (!(a.dbg_skip & 2)) cp_async16(dst0 + j * a.S + r * 16, ti.src + (size_t)i * 16);
                 r += dr;
                 j += dj;
                 if (j >= a.HC) {
@@ -148,9 +162,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
                     r++;
                 }
             }
+            if (warp == 0) TC_TRACE(0, it, 2);
             cp_async_wait_all();
             fence_proxy_async();
             mbar_arrive(smem_u32(&c->full_a[buf]));
+            if (warp == 0) TC_TRACE(0, it, 3);
         }
     } else if (warp < 8) {
         // ================= epilogue =================
@@ -162,7 +178,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             const TileInfo ti = c->info[slot];
             if (ti.nf <= 0) break;
             const int acc = it & 1;
+            if (warp == 4) TC_TRACE(1, it, 0);
             mbar_wait_spin(smem_u32(&c->tmem_full[acc]), (it >> 1) & 1);
+            if (warp == 4) TC_TRACE(1, it, 1);
             tc_fence_after();
             const uint32_t t0 = tmem + (uint32_t)(acc * ACC_STRIDE) + ((uint32_t)lane_base << 16);
             const long long* sq = a.sq + (size_t)ti.tab * a.C2p;
@@ -211,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             tc_fence_before();
             mbar_arrive(smem_u32(&c->tmem_empty[acc]));
             mbar_arrive(smem_u32(&c->info_empty[slot]));
+            if (warp == 4) TC_TRACE(1, it, 2);
         }
     } else if (warp == 8) {
         // ================= tile scheduler + B loader (whole warp in lock-step, one elected lane issues the copies) =================
@@ -250,24 +269,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             int next_tab = lane == 0 ? publish(it + 1) : 0;  // the A producers start on tile it+1 while tile it's coefficients stream
             next_tab = __shfl_sync(0xffffffffu, next_tab, 0);
             const signed char* src = a.btab + (size_t)tab * tab_bytes;
+            TC_TRACE(2, it, 0);
             int kb = kb_rot;
             for (int kbi = 0; kbi < NKB; kbi++) {
                 mbar_wait_spin(eb_bar, ph ^ 1);
+                TC_TRACE_STAGE(2, it, kbi, 0);
                 if (leader) {
-                    mbar_arrive_expect_tx(fb_bar, (uint32_t)stage_bytes);
-                    bulk_g2s(dst, src + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, fb_bar);
+                    if (a.dbg_skip & 1) {
+                        mbar_arrive(fb_bar);
+                    } else {
+                        mbar_arrive_expect_tx(fb_bar, (uint32_t)stage_bytes);
+                        bulk_g2s(dst, src + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, fb_bar);
+                    }
                 }
+                TC_TRACE_STAGE(2, it, kbi, 1);
                 if (++kb == NKB) kb = 0;
                 dst += (uint32_t)stage_bytes;
                 fb_bar += 8;
                 eb_bar += 8;
                 if (++stg == (uint32_t)a.NSTB) stg = 0, ph ^= 1, dst = smem_u32(bring), fb_bar = fb_bar0, eb_bar = eb_bar0;
             }
+            TC_TRACE(2, it, 1);
             tab = next_tab;
         }
     } else {
         // ================= MMA issuer (whole warp in lock-step, one elected lane issues) =================
-        const uint32_t leader = elect_one();
+        const uint32_t leader = (a.dbg_skip & 4) ? 0u : elect_one();
+        const uint32_t committer = elect_one();
         const uint32_t idesc = idesc_i8(128, a.NC, a.a_signed, 1);
         const int KSTEPS = a.K / 32;
         uint32_t stg = 0, ph = 0;
@@ -279,7 +307,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
         uint32_t b_lo = b_lo_ring;
         const uint32_t fb_bar0 = smem_u32(&c->full_b[0]), eb_bar0 = smem_u32(&c->empty_b[0]);
         uint32_t fb_bar = fb_bar0, eb_bar = eb_bar0;
+        uint32_t probe = 0;  // result of the early try_wait on the stage about to be consumed
         const uint32_t a_step = 2u * ((uint32_t)a.S >> 4);
+        const int spr_ks = a.HC / 2;       // k-steps per hop-row
+        const int spr = spr_ks / KBS;      // stages per hop-row (exact when a.stage_in_row)
         // k-step number kbi * KBS + ks of the tile goes to partial accumulator (kbi * KBS + ks) % NACC; the first NACC k-steps
         // overwrite (accumulate = 0)
         auto acc_col = [](int kbi, int ks) -> uint32_t { return (uint32_t)(((kbi * KBS + ks) & (NACC - 1)) * NCS); };
@@ -289,49 +320,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k1_tc_kernel(const TcArgs a) {
             mbar_wait_spin(smem_u32(&c->info_full[slot]), (it / TC_INFO_SLOTS) & 1);
             if (c->info[slot].nf <= 0) break;
             const int buf = it & 1;
+            TC_TRACE(3, it, 0);
             mbar_wait_spin(smem_u32(&c->full_a[buf]), (it >> 1) & 1);
+            TC_TRACE(3, it, 1);
             mbar_wait_spin(smem_u32(&c->tmem_empty[buf]), ((it >> 1) & 1) ^ 1);
+            TC_TRACE(3, it, 2);
             fence_proxy_async();
             tc_fence_after();
             const uint32_t d_tmem = tmem + (uint32_t)(buf * ACC_STRIDE);
             const uint32_t a_lo = (uint32_t)adesc0 + (smem_u32(abuf + buf * abuf_bytes) >> 4);
-            int ksg = kb_rot * KBS;  // k-step index inside the frame of the stage being consumed
+            // Stage `kb` of the frame covers k-steps [kb*KBS, kb*KBS + KBS).  When every stage lies inside one hop-row
+            // (a.stage_in_row) its A start offsets are base + ks * a_step with base following a two-level counter (columns
+            // inside the row, then the next row): pure uniform arithmetic, nothing loaded per stage.
+            int kb = kb_rot;
+            uint32_t base = a_lo + a.aoff[kb_rot * KBS];
+            int in_row = (kb_rot * KBS) % spr_ks / KBS;  // stage index inside its hop-row
             for (int kbi = 0; kbi < NKB; kbi++) {
-                mbar_wait_spin(fb_bar, ph);
+                // (the barrier of this stage was probed one iteration ago: its round trip overlaps the previous stage's issue)
+                if (!probe) mbar_wait_spin(fb_bar, ph);
+                {
+                    uint32_t nb = fb_bar + 8, nph = ph;
+                    if (stg + 1 == (uint32_t)a.NSTB) nb = fb_bar0, nph = ph ^ 1;
+                    probe = mbar_test(nb, nph) ? 1u : 0u;  // may be a stage of the NEXT tile: same ring, same order
+                }
+                TC_TRACE_STAGE(3, it, kbi, 0);
                 tc_fence_after();
                 if (a.stage_in_row) {
-                    // the stage's KBS k-steps lie in one hop-row: consecutive k-steps are two 16-byte columns apart
-                    const uint32_t base = a_lo + a.aoff[ksg];
-                    if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < KBS; ks++)
-                            mma_i8_split(d_tmem + acc_col(kbi, ks), base + ks * a_step, a_hi, b_lo + ks * bstep16, b_hi, idesc, acc_first(kbi, ks) ? 0u : 1u);
-                        mma_commit(eb_bar);
-                    }
+                    for (int ks = 0; ks < KBS; ks++)
+                        mma_i8_split_if(leader, d_tmem + acc_col(kbi, ks), base + ks * a_step, a_hi, b_lo + ks * bstep16, b_hi, idesc, acc_first(kbi, ks) ? 0u : 1u);
                 } else {
-                    uint32_t ao[KBS];
 #pragma unroll
-                    for (int ks = 0; ks < KBS; ks++) ao[ks] = a_lo + a.aoff[ksg + ks];
-                    if (leader) {
-#pragma unroll
-                        for (int ks = 0; ks < KBS; ks++)
-                            mma_i8_split(d_tmem + acc_col(kbi, ks), ao[ks], a_hi, b_lo + ks * bstep16, b_hi, idesc, acc_first(kbi, ks) ? 0u : 1u);
-                        mma_commit(eb_bar);
-                    }
+                    for (int ks = 0; ks < KBS; ks++)
+                        mma_i8_split_if(leader, d_tmem + acc_col(kbi, ks), a_lo + a.aoff[kb * KBS + ks], a_hi, b_lo + ks * bstep16, b_hi, idesc,
+                                        acc_first(kbi, ks) ? 0u : 1u);
                 }
-                __syncwarp();
-                ksg += KBS;
-                if (ksg == KSTEPS) ksg = 0;  // wrapped around to the start of the frame
+                mma_commit_if(committer, eb_bar);
+                TC_TRACE_STAGE(3, it, kbi, 1);
+                // next stage of the frame (wrapping around to its start)
+                if (++kb == NKB) {
+                    kb = 0;
+                    base = a_lo + a.aoff[0];
+                    in_row = 0;
+                } else if (++in_row == spr) {
+                    in_row = 0;
+                    base = base - (uint32_t)(spr - 1) * KBS * a_step + 1u;  // first column of the next hop-row (rows are 16 bytes apart)
+                } else {
+                    base += KBS * a_step;
+                }
                 b_lo += stage16;
                 fb_bar += 8;
                 eb_bar += 8;
                 if (++stg == (uint32_t)a.NSTB) stg = 0, ph ^= 1, b_lo = b_lo_ring, fb_bar = fb_bar0, eb_bar = eb_bar0;
             }
-            if (leader) {
-                mma_commit(smem_u32(&c->empty_a[buf]));
-                mma_commit(smem_u32(&c->tmem_full[buf]));
-            }
-            __syncwarp();
+            mma_commit_if(committer, smem_u32(&c->empty_a[buf]));
+            mma_commit_if(committer, smem_u32(&c->tmem_full[buf]));
+            TC_TRACE(3, it, 3);
         }
     }
     tc_fence_before();
@@ -364,7 +408,15 @@ cudaError_t tc_launch_acc(const TcArgs& args, int grid, size_t smem, cudaStream_
     return cudaErrorInvalidValue;
 }
 
+long long* g_tc_trace = nullptr;
 }  // namespace
+
+// measurement aid: copy the clock64 stamps of the last traced launches (ABG_K1_TC_TRACE set) to the host; 256*4*16*4 values
+int abg_k1tc_trace_dump(long long* out) {
+    if (!g_tc_trace) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, g_tc_trace, sizeof(long long) * 256 * 4 * 16 * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
 
 // Geometry of the tensor-core K1 for one launch group, or eligible == 0 when the group has to use the CUDA-core kernels.
 int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int digits, K1TcPlan* p) {
@@ -399,7 +451,9 @@ int abg_k1tc_plan(int fft_size, int sfmt, int hop_bytes, int max_channels, int d
     int cols = 32;
     while (cols < NC) cols <<= 1;
     p->eligible = 1; p->K = K; p->HC = HC; p->S = S; p->NC = NC; p->ND = digits; p->C2p = C2p; p->KBS = KBS; p->NSTB = nstb;
-    int nacc = 4;  // partial accumulators per tile: 2 tiles x nacc x cols <= 512 TMEM columns
+    int nacc = 1;  // partial accumulators per tile (2 tiles x nacc x cols <= 512 TMEM columns): measured no gain over 1 on B200 (MMAs into
+                   // one accumulator already run back to back, tools/tc_probe2.cu), kept selectable with ABG_K1_TC_NACC
+    if (getenv("ABG_K1_TC_NACC")) nacc = 4;
     while (nacc > 1 && 2 * nacc * cols > 512) nacc >>= 1;
     if (const char* ev = getenv("ABG_K1_TC_NACC")) nacc = std::max(1, std::min(nacc, atoi(ev) >= 4 ? 4 : (atoi(ev) >= 2 ? 2 : 1)));
     p->nacc = nacc;
@@ -458,6 +512,18 @@ cudaError_t abg_launch_k1_tc(const K1Launch& L, const K1TcPlan& p, const K1TcTab
     a.mul = a.a_signed ? 1 : 2;
     a.off = a.a_signed ? 0 : 255;
     a.rotate = 1;
+    a.dbg_skip = 0;
+    if (const char* ev = getenv("ABG_K1_TC_SKIP")) a.dbg_skip = atoi(ev);
+    a.trace = nullptr;
+    static long long* trace_buf = nullptr;  // measurement aid only: one process-wide buffer, dumped by abg_debug_k1tc_trace_dump()
+    if (getenv("ABG_K1_TC_TRACE")) {
+        if (!trace_buf) {
+            cudaMalloc((void**)&trace_buf, sizeof(long long) * 256 * 4 * 16 * 4);
+            cudaMemset(trace_buf, 0, sizeof(long long) * 256 * 4 * 16 * 4);
+        }
+        a.trace = trace_buf;
+        g_tc_trace = trace_buf;
+    }
     a.stage_in_row = ((p.HC / 2) % p.KBS == 0) ? 1 : 0;
     for (int ks = 0; ks < p.K / 32; ks++) {
         // K bytes [32ks, 32ks+32) of a frame are the two 16-byte columns j, j+1 of hop-row q

@@ -52,6 +52,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// non-blocking probe of a phase (test_wait never suspends the warp)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // Bounded wait: a barrier that never completes (a protocol bug) must not hang the GPU.  Returns false on time-out.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, long long budget_cycles = (1ll << 31)) {
     if (mbar_try_wait(bar, parity)) return true;
@@ -77,6 +89,25 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
         "@p bra WAIT_LOOP;\n\t"
         "trap;\n"
         "WAIT_DONE:\n\t}"
+        :
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+
+// Same contract, polling with the non-blocking test_wait: lower wake-up latency than the suspending try_wait, at the price
+// of issue slots (use on the single-warp critical path of a pipeline only).
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "POLL_LOOP:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra POLL_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x4000000;\n\t"
+        "@p bra POLL_LOOP;\n\t"
+        "trap;\n"
+        "POLL_DONE:\n\t}"
         :
         : "r"(bar), "r"(parity)
         : "memory");
@@ -140,6 +171,30 @@ __device__ __forceinline__ void mma_i8_split(uint32_t d_tmem, uint32_t a_lo, uin
         "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
         :
         : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// predicated forms (issue != 0 on exactly one lane of the warp): no divergent branch around the instruction, so the loop that
+// computes the operands stays warp-uniform for the compiler
+__device__ __forceinline__ void mma_i8_split_if(uint32_t issue, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(uint32_t issue, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        :
+        : "r"(bar), "r"(issue)
         : "memory");
 }
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies tcgen05.fence::before_thread_sync)

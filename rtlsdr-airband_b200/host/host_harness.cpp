@@ -102,6 +102,7 @@ struct Harness {
     std::vector<std::vector<float>> out_mix_l, out_mix_r;        // per mixer: batches x B
     std::vector<std::vector<char>> out_mix_axc;
     std::vector<int> n_mix_batches;
+    std::vector<int> mix_was_gpu;                                 // b200_mixer_is_gpu() as seen while the demod thread was alive
     std::vector<int> failed_calls;                                // disable_device_outputs stand-in: calls per device
     // O_RAWFILE stand-in: (dev, chan) -> FILE*
     struct Raw {
@@ -127,6 +128,7 @@ void consume_ready(Harness* h) {
         h->out_mix_r[m].insert(h->out_mix_r[m].end(), channel->waveout_r, channel->waveout_r + h->B);
         h->out_mix_axc[m].push_back((char)channel->axcindicate);
         h->n_mix_batches[m]++;
+        h->mix_was_gpu[m] |= b200_mixer_is_gpu(&h->mixers[m]);
         channel->state = CH_DIRTY;
     }
     for (const Harness::Raw& r : h->rawfiles) {  // process_outputs(), O_RAWFILE branch (output.cpp:519-522)
@@ -247,6 +249,7 @@ ABG_API int abh_set_mixers(void* hp, int n_mixers, const int32_t* offsets, const
     h->mix_wave.resize(n_mixers); h->mix_wave_r.resize(n_mixers);
     h->out_mix_l.resize(n_mixers); h->out_mix_r.resize(n_mixers); h->out_mix_axc.resize(n_mixers);
     h->n_mix_batches.assign(n_mixers, 0);
+    h->mix_was_gpu.assign(n_mixers, 0);
     // reserve the per-channel output arrays first: output_t.data points into mix_data
     std::vector<std::vector<int>> count(h->devs.size());
     for (size_t i = 0; i < h->devs.size(); i++) count[i].assign(h->chans[i].size(), 0);
@@ -500,7 +503,7 @@ ABG_API const float* abh_mixer_left(void* hp, int m) { return ((Harness*)hp)->ou
 ABG_API const float* abh_mixer_right(void* hp, int m) { return ((Harness*)hp)->out_mix_r[m].data(); }
 ABG_API const char* abh_mixer_axc(void* hp, int m) { return ((Harness*)hp)->out_mix_axc[m].data(); }
 ABG_API size_t abh_mixer_overruns(void* hp, int m) { return ((Harness*)hp)->mixers[m].output_overrun_count; }
-ABG_API int abh_mixer_is_gpu(void* hp, int m) { return b200_mixer_is_gpu(&((Harness*)hp)->mixers[m]); }
+ABG_API int abh_mixer_is_gpu(void* hp, int m) { return ((Harness*)hp)->mix_was_gpu[m]; }
 ABG_API int abh_failed_calls(void* hp, int dev) { return ((Harness*)hp)->failed_calls[dev]; }
 ABG_API void abh_destroy(void* hp) {
     Harness* h = (Harness*)hp;
