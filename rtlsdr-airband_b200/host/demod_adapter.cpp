@@ -77,6 +77,7 @@ struct GpuMixer {
     mixer_t* mixer;  // the reference's object; its channel receives the sums
 };
 std::vector<GpuMixer> g_gpu_mixers;  // engine mixer index -> mixer (one demod thread owns a mixer entirely, or it stays on the CPU path)
+std::vector<int> g_mixer_devs;        // engine device indices that feed a GPU-summed mixer
 }  // namespace
 
 // process_outputs() asks this before mixer_put_samples (output.cpp:533-535): inputs of a GPU-summed mixer are not put again
@@ -126,6 +127,9 @@ static int configure_gpu_mixers(abg_engine* eng, device_t* devices, int d0, int 
         offs.push_back((int32_t)flat.size());
         g_gpu_mixers.push_back(GpuMixer{mixers + m});
     }
+    g_mixer_devs.clear();
+    for (const abg_mixer_input& mi : flat)
+        if (std::find(g_mixer_devs.begin(), g_mixer_devs.end(), mi.dev) == g_mixer_devs.end()) g_mixer_devs.push_back(mi.dev);
     if (g_gpu_mixers.empty()) return ABG_OK;
     return abg_mixers_configure(eng, (int)g_gpu_mixers.size(), offs.data(), flat.data());
 }
@@ -315,7 +319,21 @@ extern "C" void* demodulate_b200(void* params) {
         }
         std::vector<int> ready_before(nd);
         for (int i = 0; i < nd; i++) ready_before[i] = abg_batches_ready(eng, i);
-        int produced = abg_run(eng, -1);
+        // The engine sums batch b of a run over the mixer inputs that have a batch b in that run, so the devices feeding a
+        // GPU-summed mixer are demodulated in lock step (the reference's mixer likewise waits for every enabled input,
+        // mixer.cpp:186-190, and gives up on a late one only after its interval): a run takes as many batches as every
+        // mixer device that still has input holds.  A device falling a whole run behind no longer holds the others up.
+        int run_batches = -1;
+        if (!g_gpu_mixers.empty()) {
+            int lo = 1 << 30, hi = 0;
+            for (int i : g_mixer_devs) {
+                const int av = abg_batches_available(eng, i);
+                hi = std::max(hi, av);
+                if (av > 0 || devices[d0 + i].input->state == INPUT_RUNNING) lo = std::min(lo, av);
+            }
+            if (lo != (1 << 30) && hi < opt.max_batches_per_run) run_batches = lo;
+        }
+        int produced = run_batches == 0 ? 0 : abg_run(eng, run_batches);
         if (produced < 0 && produced != ABG_EOVERFLOW) {
             fatal("abg_run failed");
             abg_destroy(eng);

@@ -26,6 +26,6 @@ def test_paced_source_keeps_real_time_and_does_not_overflow_a_fast_consumer():
 
 def test_slow_consumer_overflows_like_a_live_sdr():
     blk = _block(4 * 50000, seed=5)               # S16: 4 bytes per complex sample
-    bad, consumed, overflows = host.pattern_selftest(blk, cm.SFMT_S16, 2560000, 1024, repeat=12, speedup=20.0, consumer_delay_us=30000)
+    bad, consumed, overflows = host.pattern_selftest(blk, cm.SFMT_S16, 2560000, 1024, repeat=60, speedup=20.0, consumer_delay_us=30000)
     assert overflows >= 1                         # 204.8 MB/s into a 256 KiB ring drained every 30 ms
     assert bad == 0                               # everything read before the first overflow was still the right bytes
