@@ -233,6 +233,8 @@ ABG_API int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const
 /* Measurement aid: per-role clock64 stamps of the tensor-core K1 (environment variable ABG_K1_TC_TRACE set at launch time);
  * out[256 CTAs][4 roles: producer, epilogue, loader, MMA][16 tiles][4 events]. */
 ABG_API int abg_debug_k1tc_trace(long long* out);
+/* Measurement aid: 64 event counters of the K2 tile paths (copied and cleared); only the `make stats` build counts. */
+ABG_API int abg_debug_k2_stats(unsigned long long* out);
 /* Host-only: plan and coefficient table of the tensor-core K1 (fft_mode 3) for one device, as abg_create builds them
  * (window * twiddle quantised to `digits` signed 8-bit digits, in the shared-memory image the MMA reads).
  * plan[13] = {eligible, K, HC, S, NC, ND, C2p, KBS, NSTB, tmem_cols, smem_bytes, halo, nacc}; tab == NULL queries the plan only. */

@@ -183,6 +183,7 @@ struct K2Launch {
     const float* sincos_lut;  // [2][257] sin then cos (util.cpp:103-111)
 };
 cudaError_t abg_launch_k2(const K2Launch& L, cudaStream_t s);
+int abg_k2_stats_dump(unsigned long long* out);  // event counters of the ABG_K2_STATS build (k2_demod.cu)
 
 // mixer sums (reference src/mixer.cpp:133-140,189-214), defined in k2_demod.cu (compiled without FMA contraction)
 struct MixInput {

@@ -1462,6 +1462,7 @@ int abg_debug_inject_wavein(abg_engine* e, int dev, int n_batches, const float* 
 
 // measurement aid: clock64 stamps of the tensor-core K1's roles for the first 16 tiles of every CTA (set ABG_K1_TC_TRACE before
 // abg_create); out[256][4 roles][16 tiles][4 events]
+int abg_debug_k2_stats(unsigned long long* out) { return abg_k2_stats_dump(out) == 0 ? ABG_OK : fail(ABG_EINVAL, "no counters: not an ABG_K2_STATS build (make stats)"); }
 int abg_debug_k1tc_trace(long long* out) { return abg_k1tc_trace_dump(out) == 0 ? ABG_OK : fail(ABG_EINVAL, "no trace: ABG_K1_TC_TRACE was not set"); }
 
 int abg_debug_frame(abg_engine* e, int dev, const void* iq_frame, float* fftout) {
