@@ -683,10 +683,13 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     for (auto& d : e->dev)
         if (d.has_afc) e->any_afc = true;
     {
-        // K2 is a latency-bound sequential recurrence per channel: use as few channels per warp as keeps the warp count
-        // near a few per SM (less divergence between channels in different squelch states, more SMs in use)
+        // K2 is a sequential recurrence per channel.  One channel per warp (lane-parallel tiles, no divergence between
+        // channels in different squelch states) as long as that is at most 8 warps per SM sub-partition (measured on
+        // 4096 channels: K2 0.66 ms against 0.80 ms with 8 channels per warp); beyond that as few channels per warp as
+        // keeps the warp count near two per sub-partition.
         int lpw = 1;
-        while (lpw < 32 && (e->G + lpw - 1) / lpw > 592) lpw <<= 1;
+        if (e->G > 8 * 592)
+            while (lpw < 32 && (e->G + lpw - 1) / lpw > 2 * 592) lpw <<= 1;
         const char* env = getenv("ABG_K2_LPW");
         if (env && atoi(env) > 0) {
             lpw = 1;

@@ -21,6 +21,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <vector>
 
@@ -248,6 +249,7 @@ extern "C" void* demodulate_b200(void* params) {
     std::vector<float> wo, iq, mleft, mright;
     std::vector<char> axc;
     bool idle = false;  // the previous pass neither pushed, demodulated nor delivered anything
+    auto lockstep_wait_since = std::chrono::steady_clock::now();
     while (true) {
         if (bd::exit_flag()) {
             abg_destroy(eng);
@@ -322,16 +324,19 @@ extern "C" void* demodulate_b200(void* params) {
         // The engine sums batch b of a run over the mixer inputs that have a batch b in that run, so the devices feeding a
         // GPU-summed mixer are demodulated in lock step (the reference's mixer likewise waits for every enabled input,
         // mixer.cpp:186-190, and gives up on a late one only after its interval): a run takes as many batches as every
-        // mixer device that still has input holds.  A device falling a whole run behind no longer holds the others up.
+        // mixer device that still has input holds.  A running device that delivers nothing for a second no longer holds
+        // the others up (its input has stalled; the engine then sums without it, like a mixer input that is not ready).
         int run_batches = -1;
         if (!g_gpu_mixers.empty()) {
-            int lo = 1 << 30, hi = 0;
+            int lo = 1 << 30;
             for (int i : g_mixer_devs) {
                 const int av = abg_batches_available(eng, i);
-                hi = std::max(hi, av);
                 if (av > 0 || devices[d0 + i].input->state == INPUT_RUNNING) lo = std::min(lo, av);
             }
-            if (lo != (1 << 30) && hi < opt.max_batches_per_run) run_batches = lo;
+            if (lo != (1 << 30)) run_batches = lo;
+            const auto now = std::chrono::steady_clock::now();
+            if (run_batches != 0) lockstep_wait_since = now;
+            else if (now - lockstep_wait_since > std::chrono::seconds(1)) run_batches = -1;
         }
         int produced = run_batches == 0 ? 0 : abg_run(eng, run_batches);
         if (produced < 0 && produced != ABG_EOVERFLOW) {

@@ -15,7 +15,7 @@ from airband_b200 import lib  # noqa: E402
 NAMES = {0: "samples", 1: "general-path samples", 2: "tile attempts OPEN", 3: "tile attempts CLOSING", 4: "tile attempts OPENING", 5: "tile attempts CLOSED",
          6: "tile attempts ABORT", 7: "tile samples OPEN", 8: "tile samples CLOSING", 9: "tile samples OPENING", 10: "tile samples CLOSED", 11: "tile samples ABORT",
          12: "no room for a tile", 13: "CTCSS window ends in tile", 14: "post estimator not live", 15: "OPENING at buffer_size boundary", 16: "CLOSED recent_open pending",
-         17: "tiles of 8", 18: "tiles of 16", 20: "  .. state ends within 8", 21: "  .. noise-floor update within 8", 24: "refused: low_signal_abort", 25: "refused: lp division range",
+         17: "tiles of 8", 18: "tiles of 16", 20: "  .. state ends within 8", 22: "tile attempts held-CLOSED", 23: "tile samples held-CLOSED", 31: "refused: held-CLOSED ends", 21: "  .. noise-floor update within 8", 24: "refused: low_signal_abort", 25: "refused: lp division range",
          26: "refused: sqrt range", 27: "refused: has_signal false", 28: "refused: CLOSED sees signal", 29: "refused: post < tail", 30: "refused: discriminator division range",
          32: "general in CLOSED", 33: "general in OPENING", 34: "general in CLOSING", 35: "general in ABORT", 36: "general in OPEN", 40: "general: transition sample"}
 
