@@ -265,6 +265,7 @@ extern "C" void* demodulate_b200(void* params) {
         }
         bool pushed = false;
         std::vector<size_t> new_bufs(nd);
+        std::vector<char> ring_has_more(nd, 0);  // bytes of this device still wait in its ring after this pass's push
         for (int i = 0; i < nd; i++) {
             device_t* dev = devices + d0 + i;
             input_t* in = dev->input;
@@ -302,9 +303,11 @@ extern "C" void* demodulate_b200(void* params) {
                 // left the ring: with a page-locked ring abg_push is asynchronous
                 local_bufs = (local_bufs + chunk) % in->buf_size;
                 n -= chunk;
+                available -= chunk;
                 pushed = true;
             }
             new_bufs[i] = local_bufs;
+            ring_has_more[i] = available >= bpc;
         }
         for (int i = 0; i < nd; i++) {  // fparms = freqlist + freq_idx, re-read before every batch (:498)
             device_t* dev = devices + d0 + i;
@@ -331,7 +334,8 @@ extern "C" void* demodulate_b200(void* params) {
             int lo = 1 << 30;
             for (int i : g_mixer_devs) {
                 const int av = abg_batches_available(eng, i);
-                if (av > 0 || devices[d0 + i].input->state == INPUT_RUNNING) lo = std::min(lo, av);
+                // (a finished input still counts while its ring or the engine holds samples of it)
+                if (av > 0 || ring_has_more[i] || devices[d0 + i].input->state == INPUT_RUNNING) lo = std::min(lo, av);
             }
             if (lo != (1 << 30)) run_batches = lo;
             const auto now = std::chrono::steady_clock::now();
