@@ -661,7 +661,12 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
     }
 
     // ---- CUDA resources ----------------------------------------------------------------------------------------------------
-    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    {
+        const char* pe = getenv("ABG_K2_PRIO");  // measurement knob: -1 = K1's stream above K2's
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, (pe && atoi(pe) < 0) ? hi : lo));
+    }
     e->own_stream = true;
     CU(cudaHostAlloc((void**)&e->tc_status, 64, cudaHostAllocMapped));
     memset(e->tc_status, 0, 64);
@@ -670,7 +675,8 @@ int build(abg_engine* e, const abg_config* cfg, const abg_options* opt) {
         // K2's few long-running warps must get their SM slots ahead of the next run's K1 blocks
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&e->stream_b, cudaStreamNonBlocking, hi));
+        const char* pe = getenv("ABG_K2_PRIO");  // measurement knob: 0 = K2's stream at the default priority
+        CU(cudaStreamCreateWithPriority(&e->stream_b, cudaStreamNonBlocking, (pe && atoi(pe) <= 0) ? lo : hi));
     }
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&e->ev_k1[k], cudaEventDisableTiming));

@@ -20,7 +20,7 @@ def main():
     cfg, desc = bench.make_workload(wname)
     nb = 4
     raws = bench.synth_streams(cfg, nb)
-    knobs = ("ABG_K1_TC_ROTATE", "ABG_K1_TC_CAP_KB", "ABG_K1_TC_STAGE_BYTES", "ABG_K1_TC_STAGES", "ABG_K1_TC_DIGITS", "ABG_K1_TC_NACC", "ABG_K1_TC_SKIP", "FFT_MODE", "ABG_K2_LPW")
+    knobs = ("ABG_K1_TC_ROTATE", "ABG_K1_TC_CAP_KB", "ABG_K1_TC_STAGE_BYTES", "ABG_K1_TC_STAGES", "ABG_K1_TC_DIGITS", "ABG_K1_TC_NACC", "ABG_K1_TC_SKIP", "FFT_MODE", "ABG_K2_LPW", "ABG_K2_PRIO")
     for v in variants:
         for k in knobs:
             os.environ.pop(k, None)
