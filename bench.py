@@ -442,6 +442,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream(device=local_rank)
 
@@ -624,6 +626,21 @@ def main():
                 "kernel_source_sha": sha, "issue": issue,
                 "equivalent_fft_tflops": frames_per_launch * (5 * N * math.log2(N) + 2 * N) / (k1_ms * 1e-3) / 1e12,
                 "equivalent_fft_note": "nominal 5*N*log2(N)+2N flop per frame of the full FFT the reference runs; NOT executed work"}
+    # K2 (the per-channel state machine) is bound by instruction issue / dependent latency, not by bytes: report what it executed
+    k2 = {"k2_ms": k2_ms, "bound": "sequential recurrences per channel: issue / dependent-latency bound (see DESIGN.md K2)",
+          "samples_per_launch": int(sum(len(dv.channels) for dv in cfg.devices)) * NB_RUN * B}
+    if os.path.exists(tpath):
+        try:
+            k2sha = source_sha("rtlsdr-airband_b200/csrc/k2_demod.cu")
+            for cap in json.load(open(tpath)):
+                if cap.get("workload") == args.workload and cap.get("fft_path") == "k2" and cap.get("source_sha") == k2sha and cap.get("warp_instructions_per_launch"):
+                    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                    k2.update({"warp_instructions_per_launch": cap["warp_instructions_per_launch"],
+                               "warp_instructions_per_sample": cap["warp_instructions_per_launch"] / k2["samples_per_launch"],
+                               "issue_frac": cap["warp_instructions_per_launch"] / (148 * 4 * sm_mhz * 1e6 * k2_ms * 1e-3), "from": cap.get("file")})
+        except Exception:
+            pass
+    roofline["k2"] = k2
     if path == 3:
         C = max(len(dv.channels) for dv in cfg.devices)
         nc = (4 * ((2 * C + 7) // 8 * 8) + 15) // 16 * 16

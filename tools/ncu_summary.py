@@ -4,7 +4,7 @@
     python tools/ncu_summary.py --out profiles/r02_ncu_summary.txt --captures profiles/k1_captures.json \
         gpurun_out/r02_k1tc_cfg2.ncu-rep:cfg2:3 gpurun_out/r02_k2_cfg3.ncu-rep:cfg3 ...
 
-Each argument is  <report>[:<workload>[:<fft_path>]].  For every kernel in a report the selected raw metrics are printed, plus
+Each argument is  <report>[:<workload>[:<fft_path 1|2|3, or k2 for a K2 capture>]].  For every kernel in a report the selected raw metrics are printed, plus
 the ten hottest SASS instructions by stall samples (source page).  Reports of a K1 kernel given with workload and fft_path also
 produce an entry of k1_captures.json: DRAM bytes and warp instructions per launch stamped with the sha of the kernel source, which
 is what bench.py needs to put a measured `traffic` / `issue_frac` into its roofline (it refuses captures of other source versions).
@@ -32,7 +32,7 @@ KEYS = [
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
 ]
-SRC_OF = {1: "rtlsdr-airband_b200/csrc/k1_fft.cu", 2: "rtlsdr-airband_b200/csrc/k1_pruned.cu", 3: "rtlsdr-airband_b200/csrc/k1_tc.cu"}
+SRC_OF = {1: "rtlsdr-airband_b200/csrc/k1_fft.cu", 2: "rtlsdr-airband_b200/csrc/k1_pruned.cu", 3: "rtlsdr-airband_b200/csrc/k1_tc.cu", "k2": "rtlsdr-airband_b200/csrc/k2_demod.cu"}
 
 
 def sha_of(rel):
@@ -87,7 +87,7 @@ def main():
     for spec in args.reports:
         parts = spec.split(":")
         rep, workload = parts[0], (parts[1] if len(parts) > 1 else None)
-        path = int(parts[2]) if len(parts) > 2 else None
+        path = (parts[2] if parts[2] == "k2" else int(parts[2])) if len(parts) > 2 else None
         if not os.path.exists(rep):
             lines.append(f"## {rep}: missing")
             continue
