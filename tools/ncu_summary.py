@@ -100,10 +100,8 @@ def main():
                     lines.append(f"    {k:95s} {row[k]:>16s} {units.get(k, '')}")
             try:
                 dur_us = float(row["gpu__time_duration.sum"])
-                dram = float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"])
-                unit = units.get("dram__bytes_read.sum", "")
-                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
-                dram *= mult
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                dram = sum(float(row[m]) * scale.get(units.get(m, ""), 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
                 inst = float(row.get("smsp__inst_executed.sum", "nan"))
                 lines.append(f"    -> DRAM bytes per launch {dram:.0f}; warp instructions per launch {inst:.0f}")
                 if path and workload:
