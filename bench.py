@@ -507,17 +507,32 @@ def main():
         hbuf = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
         dbuf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         rates = {}
+        half = 128 << 20
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
         for name, (dst, src) in {"h2d": (dbuf, hbuf), "d2h": (hbuf, dbuf)}.items():
             best = 0.0
-            for _ in range(5):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                dst.copy_(src, non_blocking=True)
-                b.record()
+            for rep in range(10):
+                # one 256 MiB copy, and the same bytes as two concurrent 128 MiB copies on two streams (the engine keeps
+                # several ring copies in flight): the denominator is the better of the two
+                start, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 torch.cuda.synchronize()
-                best = max(best, (256 << 20) / (a.elapsed_time(b) * 1e-3) / 1e9)
+                start.record(s1)
+                s2.wait_event(start)
+                if rep % 2 == 0:
+                    with torch.cuda.stream(s1):
+                        dst.copy_(src, non_blocking=True)
+                else:
+                    with torch.cuda.stream(s1):
+                        dst[:half].copy_(src[:half], non_blocking=True)
+                    with torch.cuda.stream(s2):
+                        dst[half:].copy_(src[half:], non_blocking=True)
+                e1.record(s1)
+                e2.record(s2)
+                torch.cuda.synchronize()
+                best = max(best, (256 << 20) / (max(start.elapsed_time(e1), start.elapsed_time(e2)) * 1e-3) / 1e9)
             rates[name] = best
-        pcie = {"h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"], "how": "256 MiB pinned <-> device copy, best of 5, CUDA events"}
+        pcie = {"h2d_gbs": rates["h2d"], "d2h_gbs": rates["d2h"],
+                "how": "256 MiB pinned <-> device, best of 10 (one copy / two concurrent 128 MiB copies on two streams), CUDA events"}
         del hbuf, dbuf
 
     # ---- value: device-timed, inputs resident in HBM ----
@@ -592,6 +607,8 @@ def main():
                "timing": "wall clock around synchronised steps (includes host-side copies out of the pinned result slots)",
                "h2d_gbs_achieved": h2d_step * args.steps / dt / 1e9,
                "pcie": pcie, "pcie_frac": (h2d_step * args.steps / dt / 1e9) / pcie["h2d_gbs"] if pcie else None, "numa": numa}
+        if pcie and e2e["pcie_frac"] > 1.0:
+            e2e["pcie_note"] = "the streaming path moved bytes faster than the copy-rate probe: the probe understates this box's H2D rate"
         eng2.close()
         del pinned
 
