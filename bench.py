@@ -700,6 +700,19 @@ def main():
                        "ms_per_engine_run": ms / n_runs, "k1_ms": a1, "k2_ms": a2, "k1_path": e.fft_path(0),
                        "hbm_frac": ab / (a1 * 1e-3) / 1e9 / peaks["hbm_gbs"], "alg_bytes_per_launch": ab, "gpu_launches": int(nl),
                        "realtime_floor_msps": sum(dv.sample_rate for dv in c.devices) / 1e6}
+                # issue-slot use of the two kernels, when profiles/k1_captures.json holds ncu captures of these exact sources
+                try:
+                    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                    src_k1 = {1: "rtlsdr-airband_b200/csrc/k1_fft.cu", 2: "rtlsdr-airband_b200/csrc/k1_pruned.cu", 3: "rtlsdr-airband_b200/csrc/k1_tc.cu"}[leg["k1_path"]]
+                    want = {leg["k1_path"]: ("k1", source_sha(src_k1), a1), "k2": ("k2", source_sha("rtlsdr-airband_b200/csrc/k2_demod.cu"), a2)}
+                    for cap in (json.load(open(tpath)) if os.path.exists(tpath) else []):
+                        w_ = want.get(cap.get("fft_path"))
+                        if cap.get("workload") == name and w_ and cap.get("source_sha") == w_[1] and cap.get("warp_instructions_per_launch"):
+                            leg[w_[0] + "_issue_frac"] = cap["warp_instructions_per_launch"] / (148 * 4 * sm_hz * w_[2] * 1e-3)
+                            if w_[0] == "k1":
+                                leg["k1_dram_traffic_over_alg_bytes"] = cap["dram_bytes_per_launch"] / ab
+                except Exception:
+                    pass
                 e.close()
                 if rank == 0 and world == 1 and not args.no_parity:
                     try:
