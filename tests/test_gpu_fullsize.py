@@ -65,9 +65,13 @@ def test_cfg3_full_size_throughput_variant_snr0():
     eng.close()
 
 
-def test_cfg5_full_size_one_gpu_share():
-    """BASELINE configs[4], one GPU's share: 512 devices x 8 AM channels, fft 512 = 4096 channel chains, which puts several
-    channels on one K2 warp (the engine's lanes-per-warp rule) in production, not just under ABG_K2_LPW."""
+@pytest.mark.parametrize("lpw", [None, 8])
+def test_cfg5_full_size_one_gpu_share(lpw, monkeypatch):
+    """BASELINE configs[4], one GPU's share: 512 devices x 8 AM channels, fft 512 = 4096 channel chains.  The engine's
+    channels-per-warp rule gives every chain its own warp (the lane-parallel tiles); the second case forces 8 channels per
+    warp, the several-lanes-per-warp K2 builds that larger shares use, at the same full size."""
+    if lpw is not None:
+        monkeypatch.setenv("ABG_K2_LPW", str(lpw))
     cfg, _ = bench.make_workload("cfg5")
     assert sum(len(d.channels) for d in cfg.devices) == 4096
     raws = bench.synth_streams(cfg, NB, n_unique=4)
