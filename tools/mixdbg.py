@@ -1,3 +1,6 @@
+"""Debug aid for the GPU-summed mixers behind the C++ host adapter: runs cfg4 through host.run_host_pipeline() and
+least-squares fits every delivered mixer batch onto the per-device oracle outputs, so a missing or mis-aligned input shows up as a
+missing / shifted weight.  Run on the GPU box:  python tools/mixdbg.py"""
 import sys, os
 ROOT = "/root/repo"
 sys.path[:0] = [os.path.join(ROOT, 'rtlsdr-airband_b200', 'py'), os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests'), ROOT]
